@@ -1,0 +1,229 @@
+/*
+ * usv_b200.h — C-ABI of the B200-native stereo block-search path.
+ *
+ * This is the drop-in seam underneath the reference's C++ interfaces
+ * (`Match`, `GenerateMatchingList`/`ResolveMatchList`, `DistanceCalculator`).
+ * Everything is `extern "C"`, plain pointers and sizes; no C++/torch types.
+ * Every entry point returns an `int` status (0 = ok, <0 = error) and never
+ * throws — the reference's thread entry points use the same 0 / -1 convention
+ * (reference P/Main.cpp:818-820, 908-911).
+ *
+ * Reference items each group replaces (P/ = Unsynchronized_Stereo_Vision_Proj325/):
+ *   usv_match                      -> class Match                       P/Match.hpp:4-12
+ *   usv_match_dense_* / _templates -> GenerateMatchingList (all-pairs   P/Main.cpp:403-426
+ *                                     scoring, i-major / j-minor)  and
+ *                                     ResolveMatchList (strict-'>' =    P/Main.cpp:432-477
+ *                                     earliest minimum wins, :451)
+ *   usv_search_params.accept_*     -> `DMatchValue < 0.75` accept test  P/Main.cpp:417
+ *   distance_kind PINHOLE          -> inline disparity + pinhole        P/Main.cpp:681-694
+ *   distance_kind POWERLAW         -> power-law fit                     P/DistanceCalculator.cpp:84
+ *   usv_moving_object_distance     -> MovingObjectDistanceCalculator    P/DistanceCalculator.cpp:15-88
+ *   usv_coordinate_position        -> CooridinatePositionCalculator     P/DistanceCalculator.cpp:90-141
+ *   usv_pair_nearest / usv_stream_*-> CameraThread capture + timestamps P/Main.cpp:876-905
+ *
+ * There is NO CPU fallback behind these symbols: when no CUDA device is
+ * usable `usv_create` fails with USV_ERR_NO_DEVICE and nothing else can run.
+ */
+#ifndef USV_B200_H
+#define USV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USV_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define USV_OK 0
+#define USV_ERR_INVALID_ARG (-1)
+#define USV_ERR_CUDA (-2)
+#define USV_ERR_NO_DEVICE (-3)
+#define USV_ERR_UNSUPPORTED (-4)
+#define USV_ERR_NOMEM (-5)
+
+/* ---- enums (plain ints in the structs) --------------------------------- */
+#define USV_COST_SAD 0  /* sum |a-b|          exact u32                       */
+#define USV_COST_SSD 1  /* sum (a-b)^2        exact u32                       */
+#define USV_COST_NCC 2  /* 1 - sum ab / sqrt(sum a^2 * sum b^2)        f64     */
+#define USV_COST_ZNCC 3 /* 1 - zero-mean NCC from exact integer sums   f64     */
+
+#define USV_DIST_NONE 0
+#define USV_DIST_PINHOLE 1  /* ((201.6*4)/(disp*0.000043))/1000  P/Main.cpp:694 */
+#define USV_DIST_POWERLAW 2 /* pow((10760*pow(disp,-0.877))/3.0752, 1/0.7791)
+                               P/DistanceCalculator.cpp:84                    */
+
+#define USV_LEFT_CAM 1  /* reference `#define LeftCam true`  P/DistanceCalculator.hpp:17 */
+#define USV_RIGHT_CAM 0 /* reference `#define RightCam false` P/DistanceCalculator.hpp:18 */
+
+#define USV_NO_MATCH 0xFFFFFFFFu /* RightIndex of a window with no accepted candidate */
+#define USV_NO_DISPARITY 0xFFFFu
+
+/* ---- records ----------------------------------------------------------- */
+
+/* Bit-identical to the reference's `class Match` (16 B: u32, u32, f64). */
+typedef struct usv_match {
+  uint32_t LeftIndex;  /* window index, row-major over the window grid        */
+  uint32_t RightIndex; /* candidate index y*NXC + x' in the other frame, or
+                          USV_NO_MATCH                                        */
+  double MatchValue;   /* normalised cost, 0 = perfect (P/Main.cpp:400-401)   */
+} usv_match;
+
+/*
+ * Search specification. Window grid: x = ix*stride_x, y = iy*stride_y for all
+ * windows that fit. Candidates of the window at (x, y) lie on the same row of
+ * the other frame, enumerated in ascending x' (the reference's j-minor scan,
+ * P/Main.cpp:410):
+ *   camera_side == LEFT : x' = x - d,  d in [search_min, search_max]
+ *   camera_side == RIGHT: x' = x + d,  d in [search_min, search_max]
+ * clipped to 0 <= x' <= width - tmpl_w. The first minimum in that order wins
+ * (strict '>' replacement, P/Main.cpp:451). disp = d feeds the distance.
+ */
+typedef struct usv_search_params {
+  int32_t tmpl_w, tmpl_h;
+  int32_t search_min, search_max;
+  int32_t stride_x, stride_y;
+  int32_t cost_kind;     /* USV_COST_*  */
+  int32_t camera_side;   /* USV_LEFT_CAM / USV_RIGHT_CAM */
+  int32_t distance_kind; /* USV_DIST_*  */
+  int32_t reserved;
+  double accept_threshold; /* accept iff MatchValue < this; reference 0.75 */
+} usv_search_params;
+
+/* Frame batch layout: [n_pairs][height][row_stride] bytes, interleaved
+ * channels (CV_8UC1 / CV_8UC3 style). Device-pointer entry points need the
+ * base pointer and row_stride to be multiples of 16. */
+typedef struct usv_frame_desc {
+  int32_t width, height, channels;
+  int32_t row_stride;   /* bytes between rows            */
+  int64_t frame_stride; /* bytes between frames of a batch */
+} usv_frame_desc;
+
+/* Result arrays, one entry per (pair, window); any pointer may be NULL.
+ * All are device pointers for *_device calls and host pointers for *_host. */
+typedef struct usv_outputs {
+  usv_match *matches;      /* 16-B reference records                          */
+  uint32_t *right_index;   /* as usv_match.RightIndex                         */
+  uint32_t *raw_cost;      /* exact integer cost of the winner (SAD/SSD)      */
+  double *score;           /* NCC / ZNCC correlation of the winner            */
+  double *distance;        /* cm, f64 (reference type)                        */
+  float *distance_f32;     /* cm, f32 copy for bandwidth-bound consumers      */
+  uint16_t *disparity_u16; /* d of the winner or USV_NO_DISPARITY             */
+} usv_outputs;
+
+typedef struct usv_ctx usv_ctx;       /* one per (GPU, host thread)          */
+typedef struct usv_stream usv_stream; /* pinned ring + CUDA streams          */
+
+/* ---- lifetime ---------------------------------------------------------- */
+int usv_abi_version(void);
+int usv_create(int device, usv_ctx **out);
+int usv_destroy(usv_ctx *ctx);
+const char *usv_last_error(const usv_ctx *ctx);
+/* kernels launched by this context since creation (evidence counter) */
+int64_t usv_launch_count(const usv_ctx *ctx);
+/* name of the kernel variant the last match call dispatched to */
+const char *usv_last_kernel(const usv_ctx *ctx);
+
+/* ---- geometry (pure host arithmetic, no device needed) ------------------ */
+/* nx, ny: window grid; cand_evals: candidate evaluations per frame pair.  */
+int usv_grid_dims(const usv_frame_desc *frame, const usv_search_params *params,
+                  int32_t *nx, int32_t *ny, int64_t *cand_evals);
+
+/* ---- dense sweep: every window of the grid ------------------------------ */
+int usv_match_dense_device(usv_ctx *ctx, const uint8_t *d_left,
+                           const uint8_t *d_right, const usv_frame_desc *frame,
+                           int32_t n_pairs, const usv_search_params *params,
+                           const usv_outputs *d_out, void *cuda_stream);
+/* Host buffers: H2D, kernels, D2H and a final synchronise, all inside. */
+int usv_match_dense_host(usv_ctx *ctx, const uint8_t *h_left,
+                         const uint8_t *h_right, const usv_frame_desc *frame,
+                         int32_t n_pairs, const usv_search_params *params,
+                         const usv_outputs *h_out);
+
+/* ---- sparse templates: explicit (x, y) list, shared by all pairs -------- */
+/* cost_rows (optional): [n_pairs][n_templates][row_cap] u32 costs of every
+ * candidate in scan order (SAD/SSD); score_rows likewise f64 (NCC/ZNCC).
+ * Entries past a template's candidate count are left untouched. */
+int usv_match_templates_device(usv_ctx *ctx, const uint8_t *d_left,
+                               const uint8_t *d_right,
+                               const usv_frame_desc *frame, int32_t n_pairs,
+                               const int32_t *d_tx, const int32_t *d_ty,
+                               int32_t n_templates,
+                               const usv_search_params *params,
+                               const usv_outputs *d_out, uint32_t *d_cost_rows,
+                               double *d_score_rows, int32_t row_cap,
+                               void *cuda_stream);
+int usv_match_templates_host(usv_ctx *ctx, const uint8_t *h_left,
+                             const uint8_t *h_right,
+                             const usv_frame_desc *frame, int32_t n_pairs,
+                             const int32_t *h_tx, const int32_t *h_ty,
+                             int32_t n_templates,
+                             const usv_search_params *params,
+                             const usv_outputs *h_out, uint32_t *h_cost_rows,
+                             double *h_score_rows, int32_t row_cap);
+
+/* ---- distance family (host buffers; one tiny kernel each) ---------------- */
+int usv_disparity_to_distance(usv_ctx *ctx, const int32_t *h_disp, int64_t n,
+                              int32_t distance_kind, double *h_dist);
+
+/* MovingObjectDistanceCalculator, P/DistanceCalculator.cpp:15-88.
+ * Points are (x, y) float pairs; idx3 is (x, y, z) int triples indexing
+ * cur/old/older; timestamps are steady_clock tick counts (ns).
+ * Writes n_idx distances, or nothing (returns *n_out = 0) when any of the
+ * three other-camera histories is empty (:28). */
+int usv_moving_object_distance(usv_ctx *ctx, int32_t camera_side,
+                               int64_t t_this_ns, const float *this_xy,
+                               int32_t n_this, const float *other_xy,
+                               int32_t n_other, const float *old_xy,
+                               int32_t n_old, const float *older_xy,
+                               int32_t n_older, const int32_t *idx3,
+                               int32_t n_idx, int64_t t_other_ns,
+                               int64_t t_old_ns, int64_t t_older_ns,
+                               double *h_dist, int32_t *n_out);
+
+/* CooridinatePositionCalculator, P/DistanceCalculator.cpp:90-141 (without the
+ * CoordinateDisplay gate, which lives in the C++ wrapper). xyz: n*3 doubles. */
+int usv_coordinate_position(usv_ctx *ctx, int32_t camera_side,
+                            const double *h_dist, const float *h_xy, int64_t n,
+                            double *h_xyz);
+
+/* ---- unsynchronized capture replacement (pure host) ---------------------- */
+/* Nearest-timestamp pairing of two ascending timestamp lists (seconds):
+ * each left frame takes the right frame with the smallest |tL - tR|
+ * (earlier one on a tie), rejected when the gap exceeds max_dt; a right
+ * frame is used at most once (the closer left frame keeps it).
+ * Returns the number of pairs written (<= cap) or <0 on error. */
+int64_t usv_pair_nearest(const double *t_left, int64_t n_left,
+                         const double *t_right, int64_t n_right, double max_dt,
+                         int32_t *out_left, int32_t *out_right, int64_t cap);
+
+/* ---- streamed matching: pinned ring, cudaMemcpyAsync on n_slots streams -- */
+#define USV_OUT_MATCHES 0x01
+#define USV_OUT_RIGHT_INDEX 0x02
+#define USV_OUT_RAW_COST 0x04
+#define USV_OUT_SCORE 0x08
+#define USV_OUT_DISTANCE 0x10
+#define USV_OUT_DISTANCE_F32 0x20
+#define USV_OUT_DISPARITY_U16 0x40
+
+int usv_stream_create(usv_ctx *ctx, const usv_frame_desc *frame,
+                      const usv_search_params *params, int32_t pairs_per_slot,
+                      int32_t n_slots, uint32_t output_mask, usv_stream **out);
+int usv_stream_destroy(usv_stream *s);
+/* Pinned staging buffers of a slot: frames laid out per `frame`, outputs
+ * one entry per (pair, window). */
+int usv_stream_slot(usv_stream *s, int32_t slot, uint8_t **h_left,
+                    uint8_t **h_right, usv_outputs *h_out);
+/* Enqueue H2D + kernels + D2H for the first n_pairs of the slot. */
+int usv_stream_submit(usv_stream *s, int32_t slot, int32_t n_pairs);
+/* Block until the slot's D2H has landed. */
+int usv_stream_wait(usv_stream *s, int32_t slot);
+/* Bytes moved per submitted pair (for the bench's e2e accounting). */
+int usv_stream_bytes_per_pair(const usv_stream *s, int64_t *h2d, int64_t *d2h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USV_B200_H */

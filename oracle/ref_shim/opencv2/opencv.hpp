@@ -1,0 +1,37 @@
+// Minimal TYPE SHIM so that the reference's own translation units
+// (P/Match.cpp, P/DistanceCalculator.cpp, P/Main.cpp:432-477) compile
+// verbatim without OpenCV 3.0.0, which is not installable here.
+// Only the cv:: value types and operators those units use. Written for this
+// repo; not OpenCV code. Used solely by oracle/Makefile -> oracle/_ref/.
+#ifndef USV_ORACLE_CV_SHIM_HPP
+#define USV_ORACLE_CV_SHIM_HPP
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+namespace cv {
+template <typename T> struct Point_ {
+  T x, y;
+  Point_() : x(0), y(0) {}
+  Point_(T x_, T y_) : x(x_), y(y_) {}
+};
+template <typename T> inline Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(T(a.x + b.x), T(a.y + b.y)); }
+template <typename T> inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(T(a.x - b.x), T(a.y - b.y)); }
+// OpenCV 3.0 semantics (core/types.hpp): scale by float goes through
+// saturate_cast<T>(a.x*b) / saturate_cast<T>(a.x/b); for T=float that is a
+// plain float multiply / divide.
+template <typename T> inline Point_<T> operator*(const Point_<T>& a, float b) { return Point_<T>(T(a.x * b), T(a.y * b)); }
+template <typename T> inline Point_<T> operator/(const Point_<T>& a, float b) { return Point_<T>(T(a.x / b), T(a.y / b)); }
+template <typename T> struct Point3_ {
+  T x, y, z;
+  Point3_() : x(0), y(0), z(0) {}
+  Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
+};
+typedef Point_<int> Point2i;
+typedef Point2i Point;
+typedef Point_<float> Point2f;
+typedef Point_<double> Point2d;
+typedef Point3_<int> Point3i;
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
+}  // namespace cv
+#endif
