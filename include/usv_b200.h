@@ -216,6 +216,8 @@ int usv_stream_destroy(usv_stream *s);
  * one entry per (pair, window). */
 int usv_stream_slot(usv_stream *s, int32_t slot, uint8_t **h_left,
                     uint8_t **h_right, usv_outputs *h_out);
+/* Layout of the pinned frame buffers (128-byte row pitch, packed frames). */
+int usv_stream_frame_desc(const usv_stream *s, usv_frame_desc *out);
 /* Enqueue H2D + kernels + D2H for the first n_pairs of the slot. */
 int usv_stream_submit(usv_stream *s, int32_t slot, int32_t n_pairs);
 /* Block until the slot's D2H has landed. */

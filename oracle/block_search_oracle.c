@@ -179,7 +179,7 @@ static int match_one(const uint8_t *left, const uint8_t *right,
     window_sums(left, right, f->row_stride, f->channels, x, xr, y, p->tmpl_w,
                 p->tmpl_h, p->cost_kind, &s);
     double v = match_value(p->cost_kind, &s, n, &sc);
-    uint32_t r = p->cost_kind == USV_COST_SAD ? s.sad : s.ssd;
+    uint32_t r = p->cost_kind == USV_COST_SAD ? s.sad : p->cost_kind == USV_COST_SSD ? s.ssd : 0xFFFFFFFFu; /* raw cost is n/a for float kinds */
     if (cost_row) cost_row[xr - lo] = r;
     if (score_row) score_row[xr - lo] = sc;
     /* strict: an equal later candidate never replaces (P/Main.cpp:451) */

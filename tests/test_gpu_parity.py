@@ -1,0 +1,229 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the CPU oracle on
+the same seeded inputs and against the committed golden fixtures.
+
+Bar: bit-exact for integer costs, indices, disparities, Match records and (for
+NCC/ZNCC) the f64 scores, which are computed from exact integer sums with the
+same IEEE operations as the oracle. Distances: <= 1e-12 relative (device pow vs
+libm pow; the north-star tolerance is 1e-3)."""
+import os
+
+import numpy as np
+import pytest
+
+from unsynchronized_stereo_vision_proj325_b200 import _abi, api, synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DIST_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def assert_same(got, exp, float_kind):
+    for k in ("right_index", "raw_cost", "disparity_u16"):
+        assert np.array_equal(got[k], exp[k]), k
+    assert np.array_equal(got["matches"]["LeftIndex"], exp["matches"]["LeftIndex"])
+    assert np.array_equal(got["matches"]["RightIndex"], exp["matches"]["RightIndex"])
+    # MatchValue / score: bit-exact (inf == inf included)
+    assert got["matches"]["MatchValue"].tobytes() == exp["matches"]["MatchValue"].tobytes()
+    assert got["score"].tobytes() == exp["score"].tobytes()
+    for k in ("distance", "distance_f32"):
+        g, e = got[k].astype(np.float64), exp[k].astype(np.float64)
+        assert np.array_equal(np.isinf(g), np.isinf(e)) and np.array_equal(np.isnan(g), np.isnan(e)), k
+        fin = np.isfinite(e)
+        tol = DIST_RTOL if k == "distance" else 1e-6
+        assert np.allclose(g[fin], e[fin], rtol=tol, atol=0), k
+
+
+def _golden_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.CASES
+
+
+CASES = _golden_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_dense_vs_golden(ctx, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    kw = CASES[name][5]
+    p = _abi.make_params(**kw)
+    got = ctx.match_dense(z["left"], z["right"], p)
+    exp = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    assert_same(got, exp, kw["cost"] in ("ncc", "zncc"))
+
+
+SWEEP = [
+    # W, H, C, shift, params
+    (640, 40, 1, 37, dict(tmpl_w=16, tmpl_h=16, cost="sad")),                                   # C2 geometry, thin band
+    (640, 36, 1, 37, dict(tmpl_w=16, tmpl_h=16, cost="sad", search_max=127)),                   # D=128 variant
+    (640, 36, 1, 37, dict(tmpl_w=16, tmpl_h=16, cost="ssd", search_max=127)),
+    (320, 40, 3, 20, dict(tmpl_w=32, tmpl_h=32, cost="zncc", search_max=255, accept_threshold=0.4)),  # C3 geometry, cropped
+    (320, 40, 3, 20, dict(tmpl_w=32, tmpl_h=32, cost="ncc", search_max=63)),
+    (200, 30, 1, -15, dict(tmpl_w=16, tmpl_h=16, cost="sad", camera_side=_abi.RIGHT_CAM, search_max=64)),
+    (131, 29, 1, 9, dict(tmpl_w=7, tmpl_h=5, cost="sad", search_min=1, search_max=33)),          # ragged sizes
+    (131, 29, 2, 9, dict(tmpl_w=5, tmpl_h=3, cost="ssd", search_max=20)),                        # row bytes not /4
+    (77, 23, 4, 4, dict(tmpl_w=9, tmpl_h=9, cost="zncc", search_max=30, distance_kind=_abi.DIST_POWERLAW)),
+    (96, 33, 3, 6, dict(tmpl_w=11, tmpl_h=4, cost="sad", stride_x=2, stride_y=3, search_max=40)),
+    (64, 64, 1, 5, dict(tmpl_w=64, tmpl_h=64, cost="ssd")),                                      # one window, max template
+    (600, 24, 1, 3, dict(tmpl_w=16, tmpl_h=16, cost="sad", search_min=-8, search_max=8)),         # signed range
+]
+
+
+@pytest.mark.parametrize("w,h,c,shift,kw", SWEEP)
+def test_dense_vs_oracle(ctx, oracle, w, h, c, shift, kw):
+    left, right = synth.make_pairs(2, w, h, c, shift=shift, noise_sigma=2.0, seed=w * 7 + h)
+    p = _abi.make_params(**kw)
+    got = ctx.match_dense(left, right, p)
+    exp = oracle.match_dense(left, right, p)
+    assert_same(got, exp, kw["cost"] in ("ncc", "zncc"))
+    assert ctx.launch_count > 0
+
+
+@pytest.mark.parametrize("kind", ["sad", "ssd", "ncc", "zncc"])
+def test_templates_full_cost_rows(ctx, oracle, kind):
+    """Config C1: single 640x480 pair, shift 37, one 16x16 template at (300, 200),
+    full-row search — every candidate's cost, not only the winner."""
+    left, right = synth.make_pairs(1, 640, 480, 1, shift=37, noise_sigma=2.0, seed=325)
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost=kind)
+    tx, ty = [300, 0, 624, 37], [200, 0, 464, 100]
+    got = ctx.match_templates(left, right, tx, ty, p, rows=True)
+    exp = oracle.match_templates(left, right, tx, ty, p, rows=True)
+    assert_same(got, exp, kind in ("ncc", "zncc"))
+    if kind in ("sad", "ssd"):
+        assert np.array_equal(got["cost_rows"], exp["cost_rows"])
+    else:
+        assert got["score_rows"].tobytes() == exp["score_rows"].tobytes()
+    assert got["disparity_u16"][0, 0] == 37  # the known shift is recovered
+
+
+def test_tie_break_flat_frames(ctx, oracle):
+    left = np.full((1, 24, 128), 9, np.uint8)
+    for side in (_abi.LEFT_CAM, _abi.RIGHT_CAM):
+        for kind in ("sad", "zncc"):
+            p = _abi.make_params(tmpl_w=8, tmpl_h=8, cost=kind, camera_side=side, search_max=50, accept_threshold=2.0)
+            got = ctx.match_dense(left, left.copy(), p)
+            exp = oracle.match_dense(left, left.copy(), p)
+            assert_same(got, exp, kind == "zncc")
+
+
+def test_empty_ranges_and_threshold(ctx, oracle):
+    left, right = synth.make_pairs(1, 80, 20, 1, shift=3, noise_sigma=30.0, seed=2)
+    for kw in (dict(search_min=10, search_max=12), dict(search_min=0, search_max=6, accept_threshold=0.02)):
+        p = _abi.make_params(tmpl_w=8, tmpl_h=8, cost="sad", **kw)
+        got = ctx.match_dense(left, right, p)
+        exp = oracle.match_dense(left, right, p)
+        assert_same(got, exp, False)
+        assert (got["right_index"] == _abi.NO_MATCH).any()
+
+
+def test_unaligned_host_stride(ctx, oracle):
+    """Host frames with an odd row stride go through the repacking H2D path."""
+    rng = np.random.default_rng(4)
+    buf_l = rng.integers(0, 256, (2, 30, 101), dtype=np.uint8)
+    buf_r = rng.integers(0, 256, (2, 30, 101), dtype=np.uint8)
+    left, right = buf_l[:, :, :97], buf_r[:, :, :97]
+    p = _abi.make_params(tmpl_w=12, tmpl_h=12, cost="ssd", search_max=30)
+    got = ctx.match_dense(left, right, p)
+    exp = oracle.match_dense(np.ascontiguousarray(left), np.ascontiguousarray(right), p)
+    assert_same(got, exp, False)
+
+
+def test_invalid_arguments_fail_loudly(ctx):
+    left, right = synth.make_pairs(1, 64, 32, 1)
+    with pytest.raises(api.UsvError):
+        ctx.match_dense(left, right, _abi.make_params(tmpl_w=128, tmpl_h=8))
+    with pytest.raises(api.UsvError):
+        ctx.match_dense(left, right, _abi.make_params(tmpl_w=8, tmpl_h=8, cost=7))
+    with pytest.raises(api.UsvError):
+        ctx.match_templates(left, right, [60], [0], _abi.make_params(tmpl_w=8, tmpl_h=8))
+
+
+# ---- distance family ---------------------------------------------------------
+def test_disparity_to_distance(ctx, oracle):
+    d = np.arange(-3, 700, dtype=np.int32)
+    for kind in (_abi.DIST_PINHOLE, _abi.DIST_POWERLAW):
+        got = ctx.disparity_to_distance(d, kind)
+        exp = oracle.distance(d, kind)
+        assert np.array_equal(np.isnan(got), np.isnan(exp)) and np.array_equal(np.isinf(got), np.isinf(exp))
+        fin = np.isfinite(exp)
+        assert np.allclose(got[fin], exp[fin], rtol=DIST_RTOL, atol=0)
+    assert ctx.disparity_to_distance([40], _abi.DIST_POWERLAW)[0] == pytest.approx(556.401951467, rel=1e-11)
+
+
+MS = 1_000_000
+
+
+def test_moving_object_distance(ctx, oracle):
+    args = (110 * MS, [(300, 200)], [(260, 200)], [(250, 200)], [(240, 200)], [(0, 0, 0)], 100 * MS, 67 * MS, 33 * MS)
+    assert ctx.moving_object_distance(1, *args)[0] == pytest.approx(626.463714398, rel=1e-11)
+    rng = np.random.default_rng(7)
+    for trial in range(100):
+        n_other, n_old, n_older = (int(rng.integers(0 if trial % 10 == 0 else 1, 6)) for _ in range(3))
+        n_idx, n_this = int(rng.integers(0, 8)), int(rng.integers(0, 8))
+        t_older = int(rng.integers(0, 10**9))
+        t_old = t_older + int(rng.integers(0 if trial % 7 == 0 else 1, 50 * MS))  # zero gaps -> inf / NaN paths
+        t_other = t_old + int(rng.integers(1, 50 * MS))
+        t_this = t_other + int(rng.integers(-20 * MS, 20 * MS))
+        a = (t_this, rng.uniform(0, 640, (n_this, 2)), rng.uniform(0, 640, (n_other, 2)), rng.uniform(0, 640, (n_old, 2)),
+             rng.uniform(0, 640, (n_older, 2)), rng.integers(-1, 7, (n_idx, 3)), t_other, t_old, t_older)
+        for side in (0, 1):
+            got = ctx.moving_object_distance(side, *a)
+            exp = oracle.moving_object_distance(side, *a)
+            assert got.shape == exp.shape
+            assert np.array_equal(np.isnan(got), np.isnan(exp)) and np.array_equal(np.isinf(got), np.isinf(exp)), trial
+            fin = np.isfinite(exp)
+            assert np.allclose(got[fin], exp[fin], rtol=DIST_RTOL, atol=0), trial
+
+
+def test_coordinate_position(ctx, oracle):
+    for side, exp in ((1, (9.103702, 99.584751, 12.454575)), (0, (-18.505677, 98.272783, 8.532612))):
+        assert ctx.coordinate_position(side, [100.0], [(300, 200)])[0] == pytest.approx(exp, abs=1e-6)
+    rng = np.random.default_rng(3)
+    dist = rng.uniform(15, 2000, 500)
+    xy = np.stack([rng.uniform(0, 640, 500), rng.uniform(0, 480, 500)], 1)
+    for side in (0, 1):
+        got = ctx.coordinate_position(side, dist, xy)
+        exp = oracle.coordinate_position(side, dist, xy)
+        assert np.array_equal(np.isnan(got), np.isnan(exp))
+        fin = np.isfinite(exp)
+        assert np.allclose(got[fin], exp[fin], rtol=1e-9, atol=1e-9)
+
+
+# ---- streamed path -------------------------------------------------------------
+def test_stream_matches_oracle(ctx, oracle):
+    w, h = 160, 40
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad", search_max=63)
+    f = _abi.FrameDesc(w, h, 1, w, w * h)
+    mask = _abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST | _abi.OUT_DISTANCE_F32 | _abi.OUT_DISPARITY_U16
+    st = ctx.stream(f, p, pairs_per_slot=3, n_slots=2, mask=mask)
+    left, right = synth.make_pairs(7, w, h, 1, shift=11, noise_sigma=2.0, seed=8)
+    exp = oracle.match_dense(left, right, p)
+    batches = [(0, 3), (3, 6), (6, 7)]
+    pending = []
+    for bi, (a, b) in enumerate(batches):
+        slot = bi % 2
+        if len(pending) == 2:
+            s0, a0, b0 = pending.pop(0)
+            st.wait(s0)
+            for k in ("right_index", "raw_cost", "disparity_u16"):
+                assert np.array_equal(st.slots[s0]["out"][k][: b0 - a0], exp[k][a0:b0]), k
+        st.slots[slot]["left"][: b - a] = left[a:b]
+        st.slots[slot]["right"][: b - a] = right[a:b]
+        st.submit(slot, b - a)
+        pending.append((slot, a, b))
+    for s0, a0, b0 in pending:
+        st.wait(s0)
+        for k in ("right_index", "raw_cost", "disparity_u16"):
+            assert np.array_equal(st.slots[s0]["out"][k][: b0 - a0], exp[k][a0:b0]), k
+        assert np.allclose(st.slots[s0]["out"]["distance_f32"][: b0 - a0], exp["distance_f32"][a0:b0], rtol=1e-6)
+    assert st.h2d_bytes_per_pair == 2 * 256 * h and st.d2h_bytes_per_pair == (4 + 4 + 4 + 2) * st.nx * st.ny
+    st.close()

@@ -1,0 +1,263 @@
+"""ctypes binding of libusv_b200.so (the C-ABI in include/usv_b200.h).
+
+The library is the product; this module only marshals numpy / torch buffers
+into it. There is no CPU fallback: if the shared library is missing or no
+CUDA device is usable, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import FrameDesc, Outputs, SearchParams
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libusv_b200.so")
+
+# every symbol include/usv_b200.h declares
+EXPORTS = (
+    "usv_abi_version", "usv_create", "usv_destroy", "usv_last_error", "usv_launch_count", "usv_last_kernel",
+    "usv_grid_dims", "usv_match_dense_device", "usv_match_dense_host", "usv_match_templates_device",
+    "usv_match_templates_host", "usv_disparity_to_distance", "usv_moving_object_distance",
+    "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
+    "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_wait",
+    "usv_stream_bytes_per_pair",
+)
+
+
+class UsvError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libusv_b200.so; raise (never fall back) when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UsvError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.usv_last_error.restype = C.c_char_p
+        L.usv_last_error.argtypes = [C.c_void_p]
+        L.usv_last_kernel.restype = C.c_char_p
+        L.usv_last_kernel.argtypes = [C.c_void_p]
+        L.usv_launch_count.restype = C.c_int64
+        L.usv_launch_count.argtypes = [C.c_void_p]
+        L.usv_pair_nearest.restype = C.c_int64
+        L.usv_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.usv_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))
+
+
+def grid_dims(frame, params):
+    """(nx, ny, candidate evaluations per pair) — pure host arithmetic."""
+    nx, ny, ev = C.c_int32(), C.c_int32(), C.c_int64()
+    rc = lib().usv_grid_dims(C.byref(frame), C.byref(params), C.byref(nx), C.byref(ny), C.byref(ev))
+    if rc:
+        raise UsvError("usv_grid_dims: invalid geometry (%d)" % rc)
+    return nx.value, ny.value, ev.value
+
+
+def pair_nearest(t_left, t_right, max_dt):
+    """Host nearest-timestamp pairing (replaces the capture loop's timestamps,
+    P/Main.cpp:876-905). Returns (left_idx, right_idx) int32 arrays."""
+    tl = np.ascontiguousarray(t_left, np.float64)
+    tr = np.ascontiguousarray(t_right, np.float64)
+    cap = max(len(tl), 1)
+    ol, orr = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    n = lib().usv_pair_nearest(_ptr(tl), C.c_int64(len(tl)), _ptr(tr), C.c_int64(len(tr)), C.c_double(max_dt),
+                               _ptr(ol), _ptr(orr), C.c_int64(cap))
+    if n < 0:
+        raise UsvError("usv_pair_nearest failed (%d): timestamps must be ascending" % n)
+    return ol[:n].copy(), orr[:n].copy()
+
+
+def _alloc_host_outputs(n, mask):
+    arrs, st = {}, Outputs()
+    for name, bit, dt in _abi.OUTPUT_FIELDS:
+        if mask & bit:
+            arrs[name] = np.zeros(n, dtype=dt)
+            setattr(st, name, arrs[name].ctypes.data)
+    return arrs, st
+
+
+ALL_OUTPUTS = 0x7F
+
+
+class Context:
+    """One usv_ctx: a GPU plus its scratch buffers. Not thread-safe; create one
+    per (GPU, host thread) as the header says."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().usv_create(int(device), C.byref(self._h))
+        if rc:
+            self._h = None
+            raise UsvError("usv_create(device=%d) failed with %d (%s)" % (
+                device, rc, {-3: "no usable sm_100 CUDA device; there is no CPU fallback"}.get(rc, "see status codes")))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().usv_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc:
+            raise UsvError("%s failed (%d): %s" % (what, rc, lib().usv_last_error(self._h).decode()))
+
+    @property
+    def launch_count(self):
+        return lib().usv_launch_count(self._h)
+
+    @property
+    def last_kernel(self):
+        return lib().usv_last_kernel(self._h).decode()
+
+    # ---- host-buffer entry points -------------------------------------------
+    def match_dense(self, left, right, params, mask=ALL_OUTPUTS):
+        """left/right: [n, H, W(, C)] uint8 host arrays -> dict of [n, ny*nx]."""
+        assert left.shape == right.shape and left.strides == right.strides
+        f = _abi.frame_desc_for(left)
+        nx, ny, _ = grid_dims(f, params)
+        n = left.shape[0]
+        arrs, st = _alloc_host_outputs(n * nx * ny, mask)
+        rc = lib().usv_match_dense_host(self._h, _ptr(left), _ptr(right), C.byref(f), C.c_int32(n), C.byref(params), C.byref(st))
+        self._check(rc, "usv_match_dense_host")
+        return {k: v.reshape(n, ny * nx) for k, v in arrs.items()}
+
+    def match_templates(self, left, right, tx, ty, params, mask=ALL_OUTPUTS, rows=False):
+        assert left.shape == right.shape and left.strides == right.strides
+        f = _abi.frame_desc_for(left)
+        n, nt = left.shape[0], len(tx)
+        tx = np.ascontiguousarray(tx, np.int32)
+        ty = np.ascontiguousarray(ty, np.int32)
+        arrs, st = _alloc_host_outputs(n * nt, mask)
+        cap = f.width
+        integer = params.cost_kind <= _abi.COST_SSD
+        cost_rows = np.full((n, nt, cap), 0xFFFFFFFF, np.uint32) if rows and integer else None
+        score_rows = np.full((n, nt, cap), np.nan, np.float64) if rows and not integer else None
+        rc = lib().usv_match_templates_host(self._h, _ptr(left), _ptr(right), C.byref(f), C.c_int32(n), _ptr(tx), _ptr(ty),
+                                            C.c_int32(nt), C.byref(params), C.byref(st), _ptr(cost_rows), _ptr(score_rows),
+                                            C.c_int32(cap))
+        self._check(rc, "usv_match_templates_host")
+        out = {k: v.reshape(n, nt) for k, v in arrs.items()}
+        if rows:
+            out["cost_rows"], out["score_rows"] = cost_rows, score_rows
+        return out
+
+    # ---- device-pointer entry point (inputs resident in HBM) ------------------
+    def match_dense_device(self, d_left, d_right, frame, n_pairs, params, d_out, stream=0):
+        """Raw device pointers (ints); asynchronous on `stream` (a cudaStream_t)."""
+        rc = lib().usv_match_dense_device(self._h, _ptr(d_left), _ptr(d_right), C.byref(frame), C.c_int32(n_pairs),
+                                          C.byref(params), C.byref(d_out), C.c_void_p(int(stream)))
+        self._check(rc, "usv_match_dense_device")
+
+    # ---- distance family --------------------------------------------------------
+    def disparity_to_distance(self, disp, kind):
+        d = np.ascontiguousarray(disp, np.int32)
+        out = np.zeros(d.shape, np.float64)
+        self._check(lib().usv_disparity_to_distance(self._h, _ptr(d), C.c_int64(d.size), C.c_int32(kind), _ptr(out)),
+                    "usv_disparity_to_distance")
+        return out
+
+    def moving_object_distance(self, camera_side, t_this, this_xy, other_xy, old_xy, older_xy, idx3, t_other, t_old, t_older):
+        f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 2))  # noqa: E731
+        this_xy, other_xy, old_xy, older_xy = map(f32, (this_xy, other_xy, old_xy, older_xy))
+        idx3 = np.ascontiguousarray(np.asarray(idx3, np.int32).reshape(-1, 3))
+        out = np.zeros(max(len(idx3), 1), np.float64)
+        n_out = C.c_int32()
+        rc = lib().usv_moving_object_distance(
+            self._h, C.c_int32(int(camera_side)), C.c_int64(int(t_this)), _ptr(this_xy), C.c_int32(len(this_xy)),
+            _ptr(other_xy), C.c_int32(len(other_xy)), _ptr(old_xy), C.c_int32(len(old_xy)), _ptr(older_xy),
+            C.c_int32(len(older_xy)), _ptr(idx3), C.c_int32(len(idx3)), C.c_int64(int(t_other)), C.c_int64(int(t_old)),
+            C.c_int64(int(t_older)), _ptr(out), C.byref(n_out))
+        self._check(rc, "usv_moving_object_distance")
+        return out[:n_out.value]
+
+    def coordinate_position(self, camera_side, dist, xy):
+        dist = np.ascontiguousarray(dist, np.float64)
+        xy = np.ascontiguousarray(np.asarray(xy, np.float32).reshape(-1, 2))
+        out = np.zeros((len(dist), 3), np.float64)
+        self._check(lib().usv_coordinate_position(self._h, C.c_int32(int(camera_side)), _ptr(dist), _ptr(xy),
+                                                  C.c_int64(len(dist)), _ptr(out)), "usv_coordinate_position")
+        return out
+
+    def stream(self, frame, params, pairs_per_slot, n_slots=3, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST):
+        return Stream(self, frame, params, pairs_per_slot, n_slots, mask)
+
+
+class Stream:
+    """Pinned ring of slots; each slot owns a CUDA stream: H2D -> kernels -> D2H
+    overlap across slots (the replacement for the two capture threads)."""
+
+    def __init__(self, ctx, frame, params, pairs_per_slot, n_slots, mask):
+        self.ctx, self.params, self.mask = ctx, params, mask
+        self.pairs_per_slot, self.n_slots = pairs_per_slot, n_slots
+        self._h = C.c_void_p()
+        rc = lib().usv_stream_create(ctx._h, C.byref(frame), C.byref(params), C.c_int32(pairs_per_slot), C.c_int32(n_slots),
+                                     C.c_uint32(mask), C.byref(self._h))
+        ctx._check(rc, "usv_stream_create")
+        self.frame = FrameDesc()
+        lib().usv_stream_frame_desc(self._h, C.byref(self.frame))
+        self.nx, self.ny, self.cand_evals = grid_dims(frame, params)
+        h2d, d2h = C.c_int64(), C.c_int64()
+        lib().usv_stream_bytes_per_pair(self._h, C.byref(h2d), C.byref(d2h))
+        self.h2d_bytes_per_pair, self.d2h_bytes_per_pair = h2d.value, d2h.value
+        self.slots = [self._slot_views(i) for i in range(n_slots)]
+
+    def _slot_views(self, i):
+        hl, hr, ho = C.c_void_p(), C.c_void_p(), Outputs()
+        lib().usv_stream_slot(self._h, C.c_int32(i), C.byref(hl), C.byref(hr), C.byref(ho))
+        f = self.frame
+        nbytes = f.frame_stride * self.pairs_per_slot
+
+        def view(p):
+            buf = (C.c_uint8 * nbytes).from_address(p.value)
+            a = np.frombuffer(buf, np.uint8).reshape(self.pairs_per_slot, f.height, f.row_stride)
+            return a[:, :, : f.width * f.channels]
+
+        outs = {}
+        n_res = self.nx * self.ny * self.pairs_per_slot
+        for name, bit, dt in _abi.OUTPUT_FIELDS:
+            p = getattr(ho, name)
+            if (self.mask & bit) and p:
+                buf = (C.c_uint8 * (n_res * dt.itemsize)).from_address(p)
+                outs[name] = np.frombuffer(buf, dt).reshape(self.pairs_per_slot, self.ny * self.nx)
+        return {"left": view(hl), "right": view(hr), "out": outs}
+
+    def submit(self, slot, n_pairs=None):
+        n = self.pairs_per_slot if n_pairs is None else n_pairs
+        self.ctx._check(lib().usv_stream_submit(self._h, C.c_int32(slot), C.c_int32(n)), "usv_stream_submit")
+
+    def wait(self, slot):
+        self.ctx._check(lib().usv_stream_wait(self._h, C.c_int32(slot)), "usv_stream_wait")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.slots = []
+            lib().usv_stream_destroy(self._h)
+            self._h = None
+
+    __del__ = close

@@ -1,0 +1,625 @@
+// usv_capi.cu — the C-ABI of include/usv_b200.h: context, validation, kernel
+// dispatch, host-buffer paths, the pinned streaming ring and host pairing.
+// No CPU compute path exists here: without a CUDA device usv_create fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "usv_common.cuh"
+
+namespace usv {
+cudaError_t launch_direct(const DevJob& J, int n_pairs, cudaStream_t st);
+// returns cudaErrorNotSupported when the dense kernels do not cover the job
+cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches);
+cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
+cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
+cudaError_t launch_moving_object_distance(int camera_side, long long t_this, const float* this_xy, int n_this, const float* other_xy,
+                                          int n_other, const float* old_xy, int n_old, const float* older_xy, int n_older,
+                                          const int* idx3, int n_idx, long long t_other, long long t_old, long long t_older,
+                                          double* out, cudaStream_t st);
+cudaError_t launch_coordinate_position(int camera_side, const double* dist, const float* xy, long long n, double* xyz, cudaStream_t st);
+}  // namespace usv
+
+using usv::DevJob;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct usv_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;  // used by the *_host entry points
+  char err[512] = {0};
+  std::atomic<long long> launches{0};
+  const char* last_kernel = "none";
+  // distance LUT cache (by kind), [lut_n] doubles
+  double* lut[3] = {nullptr, nullptr, nullptr};
+  int lut_n[3] = {0, 0, 0};
+  // grow-only scratch for the host paths
+  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[7], misc[8];
+};
+
+static const size_t kOutElem[7] = {sizeof(usv_match), 4, 4, 8, 8, 4, 2};
+
+static int fail(usv_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int grow(usv_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return USV_OK;
+  if (b.p) CU(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) return fail(ctx, USV_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+  b.cap = want;
+  return USV_OK;
+}
+
+static void** out_slot(usv_outputs* o, int i) {
+  switch (i) {
+    case 0: return (void**)&o->matches;
+    case 1: return (void**)&o->right_index;
+    case 2: return (void**)&o->raw_cost;
+    case 3: return (void**)&o->score;
+    case 4: return (void**)&o->distance;
+    case 5: return (void**)&o->distance_f32;
+    default: return (void**)&o->disparity_u16;
+  }
+}
+
+// ---- validation + job construction ---------------------------------------------
+static int check_common(usv_ctx* ctx, const usv_frame_desc* f, const usv_search_params* p, int32_t n_pairs) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (!f || !p) return fail(ctx, USV_ERR_INVALID_ARG, "null frame/params");
+  if (n_pairs < 0 || n_pairs > 65535) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d out of [0, 65535]", n_pairs);
+  if (f->width <= 0 || f->height <= 0 || f->channels < 1 || f->channels > 4)
+    return fail(ctx, USV_ERR_INVALID_ARG, "bad frame %dx%dx%d", f->width, f->height, f->channels);
+  if (f->row_stride < f->width * f->channels) return fail(ctx, USV_ERR_INVALID_ARG, "row_stride %d < width*channels", f->row_stride);
+  if (n_pairs > 1 && f->frame_stride < (int64_t)f->row_stride * f->height)
+    return fail(ctx, USV_ERR_INVALID_ARG, "frame_stride smaller than one frame");
+  if (p->tmpl_w <= 0 || p->tmpl_h <= 0 || p->tmpl_w > f->width || p->tmpl_h > f->height)
+    return fail(ctx, USV_ERR_INVALID_ARG, "template %dx%d does not fit frame %dx%d", p->tmpl_w, p->tmpl_h, f->width, f->height);
+  if ((int64_t)p->tmpl_w * p->tmpl_h * f->channels > 32768)
+    return fail(ctx, USV_ERR_UNSUPPORTED, "template of %lld bytes exceeds 32768 (u32 cost accumulators)",
+                (long long)p->tmpl_w * p->tmpl_h * f->channels);
+  if (p->tmpl_w * f->channels > 1024) return fail(ctx, USV_ERR_UNSUPPORTED, "template row wider than 1024 bytes");
+  if (p->stride_x <= 0 || p->stride_y <= 0) return fail(ctx, USV_ERR_INVALID_ARG, "stride must be positive");
+  if (p->search_min > p->search_max) return fail(ctx, USV_ERR_INVALID_ARG, "search_min > search_max");
+  if (p->search_min < -(1 << 24) || p->search_max > (1 << 24)) return fail(ctx, USV_ERR_INVALID_ARG, "search range beyond +-2^24");
+  if (p->cost_kind < USV_COST_SAD || p->cost_kind > USV_COST_ZNCC) return fail(ctx, USV_ERR_INVALID_ARG, "unknown cost_kind %d", p->cost_kind);
+  if (p->distance_kind < USV_DIST_NONE || p->distance_kind > USV_DIST_POWERLAW)
+    return fail(ctx, USV_ERR_INVALID_ARG, "unknown distance_kind %d", p->distance_kind);
+  if (p->camera_side != USV_LEFT_CAM && p->camera_side != USV_RIGHT_CAM) return fail(ctx, USV_ERR_INVALID_ARG, "camera_side must be 0 or 1");
+  return USV_OK;
+}
+
+static void fill_job(DevJob& J, const uint8_t* l, const uint8_t* r, const usv_frame_desc* f, const usv_search_params* p,
+                     const usv_outputs* o) {
+  memset(&J, 0, sizeof(J));
+  J.left = l; J.right = r;
+  J.frame_stride = f->frame_stride;
+  J.width = f->width; J.height = f->height; J.channels = f->channels; J.row_stride = f->row_stride;
+  J.tw = p->tmpl_w; J.th = p->tmpl_h; J.dmin = p->search_min; J.dmax = p->search_max;
+  J.sx = p->stride_x; J.sy = p->stride_y;
+  J.cost_kind = p->cost_kind; J.camera_side = p->camera_side; J.distance_kind = p->distance_kind;
+  J.nxc = f->width - p->tmpl_w + 1; J.nyc = f->height - p->tmpl_h + 1;
+  J.nx = (J.nxc - 1) / p->stride_x + 1; J.ny = (J.nyc - 1) / p->stride_y + 1;
+  J.row_bytes = p->tmpl_w * f->channels;
+  J.n_elems = p->tmpl_w * p->tmpl_h * f->channels;
+  J.accept_threshold = p->accept_threshold;
+  J.n_templates = J.nx * J.ny;
+  if (o) J.out = *o;
+}
+
+static int ensure_lut(usv_ctx* ctx, int kind, int width, cudaStream_t st, const double** lut) {
+  *lut = nullptr;
+  if (kind == USV_DIST_NONE) return USV_OK;
+  if (ctx->lut_n[kind] < width) {
+    // (re)build on the device with the same device function the kernels use
+    if (ctx->lut[kind]) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx->lut[kind])); ctx->lut[kind] = nullptr; }
+    int n = width < 4096 ? 4096 : width;
+    CU(cudaMalloc((void**)&ctx->lut[kind], sizeof(double) * n));
+    CU(usv::launch_build_distance_lut(ctx->lut[kind], n, kind, st));
+    CU(cudaStreamSynchronize(st));  // one-time; other streams of this context may read it next
+    ctx->launches++;
+    ctx->lut_n[kind] = n;
+  }
+  *lut = ctx->lut[kind];
+  return USV_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- lifetime ---------------------------------------------------------------------
+extern "C" int usv_abi_version(void) { return USV_ABI_VERSION; }
+
+extern "C" int usv_create(int device, usv_ctx** out) {
+  if (!out) return USV_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) return USV_ERR_NO_DEVICE;  // no CPU fallback: fail loudly
+  if (device < 0 || device >= n) return USV_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return USV_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return USV_ERR_CUDA;
+  if (prop.major < 10) return USV_ERR_NO_DEVICE;  // sm_100a cubins only
+  usv_ctx* c = new (std::nothrow) usv_ctx();
+  if (!c) return USV_ERR_NOMEM;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return USV_ERR_CUDA; }
+  *out = c;
+  return USV_OK;
+}
+
+extern "C" int usv_destroy(usv_ctx* ctx) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->in_l, &ctx->in_r, &ctx->tx, &ctx->ty, &ctx->rows_u32, &ctx->rows_f64};
+  for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  for (auto& b : ctx->out) if (b.p) cudaFree(b.p);
+  for (auto& b : ctx->misc) if (b.p) cudaFree(b.p);
+  for (double* l : ctx->lut) if (l) cudaFree(l);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return USV_OK;
+}
+
+extern "C" const char* usv_last_error(const usv_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" int64_t usv_launch_count(const usv_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : -1; }
+extern "C" const char* usv_last_kernel(const usv_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+
+extern "C" int usv_grid_dims(const usv_frame_desc* f, const usv_search_params* p, int32_t* nx, int32_t* ny, int64_t* cand_evals) {
+  if (!f || !p) return USV_ERR_INVALID_ARG;
+  int nxc = f->width - p->tmpl_w + 1, nyc = f->height - p->tmpl_h + 1;
+  if (nxc <= 0 || nyc <= 0 || p->stride_x <= 0 || p->stride_y <= 0) return USV_ERR_INVALID_ARG;
+  int gx = (nxc - 1) / p->stride_x + 1, gy = (nyc - 1) / p->stride_y + 1;
+  int64_t per_row = 0;
+  for (int ix = 0; ix < gx; ++ix) {
+    int lo, hi;
+    usv::cand_range(ix * p->stride_x, nxc, p->camera_side, p->search_min, p->search_max, &lo, &hi);
+    if (hi >= lo) per_row += hi - lo + 1;
+  }
+  if (nx) *nx = gx;
+  if (ny) *ny = gy;
+  if (cand_evals) *cand_evals = per_row * gy;
+  return USV_OK;
+}
+
+// ---- matching: device pointers -----------------------------------------------------
+static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, const usv_frame_desc* f, int32_t n_pairs,
+                        const usv_search_params* p, const usv_outputs* d_out, const int32_t* d_tx, const int32_t* d_ty,
+                        int32_t n_templates, uint32_t* d_cost_rows, double* d_score_rows, int32_t row_cap, cudaStream_t st) {
+  int rc = check_common(ctx, f, p, n_pairs);
+  if (rc) return rc;
+  if (!d_left || !d_right || !d_out) return fail(ctx, USV_ERR_INVALID_ARG, "null device pointer");
+  if (!aligned16(d_left) || !aligned16(d_right) || (f->row_stride & 15) || (f->frame_stride & 15))
+    return fail(ctx, USV_ERR_INVALID_ARG, "device frames need 16-byte aligned base, row_stride and frame_stride");
+  if (n_pairs == 0) return USV_OK;
+  CU(cudaSetDevice(ctx->device));
+  DevJob J;
+  fill_job(J, d_left, d_right, f, p, d_out);
+  const bool sparse = d_tx != nullptr;
+  if (sparse) {
+    if (!d_ty || n_templates < 0) return fail(ctx, USV_ERR_INVALID_ARG, "bad template list");
+    if (n_templates == 0) return USV_OK;
+    J.tx = d_tx; J.ty = d_ty; J.n_templates = n_templates;
+    J.cost_rows = d_cost_rows; J.score_rows = d_score_rows; J.row_cap = row_cap;
+    if ((d_cost_rows || d_score_rows) && row_cap <= 0) return fail(ctx, USV_ERR_INVALID_ARG, "row_cap must be positive");
+  }
+  if (J.out.distance || J.out.distance_f32) {
+    rc = ensure_lut(ctx, p->distance_kind, f->width, st, &J.dist_lut);
+    if (rc) return rc;
+  }
+  if (!sparse) {
+    const char* name = nullptr;
+    int nl = 0;
+    cudaError_t e = usv::launch_dense(J, n_pairs, st, &name, &nl);
+    if (e == cudaSuccess) {
+      ctx->launches += nl;
+      ctx->last_kernel = name;
+      return USV_OK;
+    }
+    if (e != cudaErrorNotSupported) return fail(ctx, USV_ERR_CUDA, "dense launch: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+  }
+  cudaError_t e = usv::launch_direct(J, n_pairs, st);
+  if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "direct launch: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  ctx->last_kernel = "block_cost_argmin_direct";
+  return USV_OK;
+}
+
+extern "C" int usv_match_dense_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, const usv_frame_desc* frame,
+                                      int32_t n_pairs, const usv_search_params* params, const usv_outputs* d_out, void* cuda_stream) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  return match_device(ctx, d_left, d_right, frame, n_pairs, params, d_out, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                      (cudaStream_t)cuda_stream);
+}
+
+extern "C" int usv_match_templates_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, const usv_frame_desc* frame,
+                                          int32_t n_pairs, const int32_t* d_tx, const int32_t* d_ty, int32_t n_templates,
+                                          const usv_search_params* params, const usv_outputs* d_out, uint32_t* d_cost_rows,
+                                          double* d_score_rows, int32_t row_cap, void* cuda_stream) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (!d_tx) return fail(ctx, USV_ERR_INVALID_ARG, "null template list");
+  return match_device(ctx, d_left, d_right, frame, n_pairs, params, d_out, d_tx, d_ty, n_templates, d_cost_rows, d_score_rows,
+                      row_cap, (cudaStream_t)cuda_stream);
+}
+
+// ---- matching: host pointers (H2D + kernels + D2H + sync inside) --------------------
+static int upload_frames(usv_ctx* ctx, DevBuf& dst, const uint8_t* h, const usv_frame_desc* f, int n_pairs, usv_frame_desc* df,
+                         cudaStream_t st) {
+  const int row_bytes = f->width * f->channels;
+  const int pitch = (row_bytes + 127) & ~127;
+  df->width = f->width; df->height = f->height; df->channels = f->channels;
+  df->row_stride = pitch; df->frame_stride = (int64_t)pitch * f->height;
+  int rc = grow(ctx, dst, (size_t)df->frame_stride * n_pairs);
+  if (rc) return rc;
+  if (n_pairs == 1 || f->frame_stride == (int64_t)f->row_stride * f->height) {
+    CU(cudaMemcpy2DAsync(dst.p, pitch, h, f->row_stride, row_bytes, (size_t)f->height * n_pairs, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int i = 0; i < n_pairs; ++i)
+      CU(cudaMemcpy2DAsync((uint8_t*)dst.p + (size_t)i * df->frame_stride, pitch, h + (size_t)i * f->frame_stride, f->row_stride,
+                           row_bytes, f->height, cudaMemcpyHostToDevice, st));
+  }
+  return USV_OK;
+}
+
+static int match_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_right, const usv_frame_desc* f, int32_t n_pairs,
+                      const usv_search_params* p, const usv_outputs* h_out, const int32_t* h_tx, const int32_t* h_ty,
+                      int32_t n_templates, uint32_t* h_cost_rows, double* h_score_rows, int32_t row_cap) {
+  int rc = check_common(ctx, f, p, n_pairs);
+  if (rc) return rc;
+  if (!h_left || !h_right || !h_out) return fail(ctx, USV_ERR_INVALID_ARG, "null host pointer");
+  if (n_pairs == 0) return USV_OK;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool sparse = h_tx != nullptr;
+  int64_t n_win;
+  if (sparse) {
+    if (!h_ty || n_templates < 0) return fail(ctx, USV_ERR_INVALID_ARG, "bad template list");
+    const int nxc = f->width - p->tmpl_w + 1, nyc = f->height - p->tmpl_h + 1;
+    for (int i = 0; i < n_templates; ++i)
+      if (h_tx[i] < 0 || h_tx[i] >= nxc || h_ty[i] < 0 || h_ty[i] >= nyc)
+        return fail(ctx, USV_ERR_INVALID_ARG, "template %d at (%d,%d) outside the frame", i, h_tx[i], h_ty[i]);
+    n_win = n_templates;
+    if (n_templates == 0) return USV_OK;
+  } else {
+    int32_t nx, ny;
+    if (usv_grid_dims(f, p, &nx, &ny, nullptr)) return fail(ctx, USV_ERR_INVALID_ARG, "bad geometry");
+    n_win = (int64_t)nx * ny;
+  }
+  const int64_t n_res = n_win * n_pairs;
+  usv_frame_desc df;
+  if ((rc = upload_frames(ctx, ctx->in_l, h_left, f, n_pairs, &df, st))) return rc;
+  if ((rc = upload_frames(ctx, ctx->in_r, h_right, f, n_pairs, &df, st))) return rc;
+  usv_outputs d_out;
+  memset(&d_out, 0, sizeof(d_out));
+  usv_outputs ho = *h_out;
+  for (int i = 0; i < 7; ++i) {
+    if (*out_slot(&ho, i)) {
+      if ((rc = grow(ctx, ctx->out[i], kOutElem[i] * n_res))) return rc;
+      *out_slot(&d_out, i) = ctx->out[i].p;
+    }
+  }
+  int32_t *d_tx = nullptr, *d_ty = nullptr;
+  uint32_t* d_rows = nullptr;
+  double* d_srows = nullptr;
+  if (sparse) {
+    if ((rc = grow(ctx, ctx->tx, sizeof(int32_t) * n_templates))) return rc;
+    if ((rc = grow(ctx, ctx->ty, sizeof(int32_t) * n_templates))) return rc;
+    d_tx = (int32_t*)ctx->tx.p; d_ty = (int32_t*)ctx->ty.p;
+    CU(cudaMemcpyAsync(d_tx, h_tx, sizeof(int32_t) * n_templates, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ty, h_ty, sizeof(int32_t) * n_templates, cudaMemcpyHostToDevice, st));
+    if (h_cost_rows) {
+      if ((rc = grow(ctx, ctx->rows_u32, sizeof(uint32_t) * n_res * row_cap))) return rc;
+      d_rows = (uint32_t*)ctx->rows_u32.p;
+      CU(cudaMemcpyAsync(d_rows, h_cost_rows, sizeof(uint32_t) * n_res * row_cap, cudaMemcpyHostToDevice, st));
+    }
+    if (h_score_rows) {
+      if ((rc = grow(ctx, ctx->rows_f64, sizeof(double) * n_res * row_cap))) return rc;
+      d_srows = (double*)ctx->rows_f64.p;
+      CU(cudaMemcpyAsync(d_srows, h_score_rows, sizeof(double) * n_res * row_cap, cudaMemcpyHostToDevice, st));
+    }
+  }
+  rc = match_device(ctx, (const uint8_t*)ctx->in_l.p, (const uint8_t*)ctx->in_r.p, &df, n_pairs, p, &d_out, d_tx, d_ty, n_templates,
+                    d_rows, d_srows, row_cap, st);
+  if (rc) return rc;
+  for (int i = 0; i < 7; ++i)
+    if (*out_slot(&ho, i)) CU(cudaMemcpyAsync(*out_slot(&ho, i), ctx->out[i].p, kOutElem[i] * n_res, cudaMemcpyDeviceToHost, st));
+  if (d_rows) CU(cudaMemcpyAsync(h_cost_rows, d_rows, sizeof(uint32_t) * n_res * row_cap, cudaMemcpyDeviceToHost, st));
+  if (d_srows) CU(cudaMemcpyAsync(h_score_rows, d_srows, sizeof(double) * n_res * row_cap, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return USV_OK;
+}
+
+extern "C" int usv_match_dense_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_right, const usv_frame_desc* frame,
+                                    int32_t n_pairs, const usv_search_params* params, const usv_outputs* h_out) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  return match_host(ctx, h_left, h_right, frame, n_pairs, params, h_out, nullptr, nullptr, 0, nullptr, nullptr, 0);
+}
+
+extern "C" int usv_match_templates_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_right, const usv_frame_desc* frame,
+                                        int32_t n_pairs, const int32_t* h_tx, const int32_t* h_ty, int32_t n_templates,
+                                        const usv_search_params* params, const usv_outputs* h_out, uint32_t* h_cost_rows,
+                                        double* h_score_rows, int32_t row_cap) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (!h_tx) return fail(ctx, USV_ERR_INVALID_ARG, "null template list");
+  return match_host(ctx, h_left, h_right, frame, n_pairs, params, h_out, h_tx, h_ty, n_templates, h_cost_rows, h_score_rows, row_cap);
+}
+
+// ---- distance family ------------------------------------------------------------------
+static int up(usv_ctx* ctx, DevBuf& b, const void* h, size_t bytes) {
+  int rc = grow(ctx, b, bytes ? bytes : 16);
+  if (rc) return rc;
+  if (bytes) CU(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return USV_OK;
+}
+
+extern "C" int usv_disparity_to_distance(usv_ctx* ctx, const int32_t* h_disp, int64_t n, int32_t kind, double* h_dist) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && (!h_disp || !h_dist))) return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  if (kind != USV_DIST_PINHOLE && kind != USV_DIST_POWERLAW) return fail(ctx, USV_ERR_INVALID_ARG, "unknown distance_kind %d", kind);
+  if (n == 0) return USV_OK;
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = up(ctx, ctx->misc[0], h_disp, sizeof(int32_t) * n))) return rc;
+  if ((rc = grow(ctx, ctx->misc[1], sizeof(double) * n))) return rc;
+  CU(usv::launch_disparity_to_distance((const int*)ctx->misc[0].p, n, kind, (double*)ctx->misc[1].p, ctx->stream));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(h_dist, ctx->misc[1].p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return USV_OK;
+}
+
+extern "C" int usv_moving_object_distance(usv_ctx* ctx, int32_t camera_side, int64_t t_this_ns, const float* this_xy, int32_t n_this,
+                                          const float* other_xy, int32_t n_other, const float* old_xy, int32_t n_old,
+                                          const float* older_xy, int32_t n_older, const int32_t* idx3, int32_t n_idx,
+                                          int64_t t_other_ns, int64_t t_old_ns, int64_t t_older_ns, double* h_dist, int32_t* n_out) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n_this < 0 || n_other < 0 || n_old < 0 || n_older < 0 || n_idx < 0) return fail(ctx, USV_ERR_INVALID_ARG, "negative count");
+  if (n_out) *n_out = 0;
+  // P/DistanceCalculator.cpp:28 — nothing is produced unless all three histories are non-empty
+  if (n_other == 0 || n_old == 0 || n_older == 0 || n_idx == 0) return USV_OK;
+  if (!other_xy || !old_xy || !older_xy || !idx3 || !h_dist || (n_this > 0 && !this_xy))
+    return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = up(ctx, ctx->misc[0], this_xy, sizeof(float) * 2 * n_this))) return rc;
+  if ((rc = up(ctx, ctx->misc[1], other_xy, sizeof(float) * 2 * n_other))) return rc;
+  if ((rc = up(ctx, ctx->misc[2], old_xy, sizeof(float) * 2 * n_old))) return rc;
+  if ((rc = up(ctx, ctx->misc[3], older_xy, sizeof(float) * 2 * n_older))) return rc;
+  if ((rc = up(ctx, ctx->misc[4], idx3, sizeof(int32_t) * 3 * n_idx))) return rc;
+  if ((rc = grow(ctx, ctx->misc[5], sizeof(double) * n_idx))) return rc;
+  CU(usv::launch_moving_object_distance(camera_side, t_this_ns, (const float*)ctx->misc[0].p, n_this, (const float*)ctx->misc[1].p,
+                                        n_other, (const float*)ctx->misc[2].p, n_old, (const float*)ctx->misc[3].p, n_older,
+                                        (const int*)ctx->misc[4].p, n_idx, t_other_ns, t_old_ns, t_older_ns,
+                                        (double*)ctx->misc[5].p, ctx->stream));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(h_dist, ctx->misc[5].p, sizeof(double) * n_idx, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (n_out) *n_out = n_idx;
+  return USV_OK;
+}
+
+extern "C" int usv_coordinate_position(usv_ctx* ctx, int32_t camera_side, const double* h_dist, const float* h_xy, int64_t n,
+                                       double* h_xyz) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && (!h_dist || !h_xy || !h_xyz))) return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  if (n == 0) return USV_OK;
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = up(ctx, ctx->misc[0], h_dist, sizeof(double) * n))) return rc;
+  if ((rc = up(ctx, ctx->misc[1], h_xy, sizeof(float) * 2 * n))) return rc;
+  if ((rc = grow(ctx, ctx->misc[2], sizeof(double) * 3 * n))) return rc;
+  CU(usv::launch_coordinate_position(camera_side, (const double*)ctx->misc[0].p, (const float*)ctx->misc[1].p, n,
+                                     (double*)ctx->misc[2].p, ctx->stream));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(h_xyz, ctx->misc[2].p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return USV_OK;
+}
+
+// ---- nearest-timestamp pairing (pure host, O(nL + nR)) ---------------------------------
+extern "C" int64_t usv_pair_nearest(const double* tl, int64_t nl, const double* tr, int64_t nr, double max_dt, int32_t* out_l,
+                                    int32_t* out_r, int64_t cap) {
+  if (nl < 0 || nr < 0 || cap < 0 || (nl > 0 && !tl) || (nr > 0 && !tr) || (cap > 0 && (!out_l || !out_r))) return USV_ERR_INVALID_ARG;
+  if (nl > INT32_MAX || nr > INT32_MAX) return USV_ERR_INVALID_ARG;
+  for (int64_t i = 1; i < nl; ++i) if (tl[i] < tl[i - 1]) return USV_ERR_INVALID_ARG;  // must be ascending
+  for (int64_t i = 1; i < nr; ++i) if (tr[i] < tr[i - 1]) return USV_ERR_INVALID_ARG;
+  int64_t n = 0, p = 0;
+  // group state: left frames that picked the same right frame are contiguous
+  int64_t g_right = -1, g_left = -1;
+  double g_gap = 0.0;
+  auto flush = [&]() -> bool {
+    if (g_right < 0) return true;
+    if (n >= cap) return false;
+    out_l[n] = (int32_t)g_left; out_r[n] = (int32_t)g_right; ++n;
+    g_right = -1;
+    return true;
+  };
+  for (int64_t i = 0; i < nl && nr > 0; ++i) {
+    while (p < nr && tr[p] < tl[i]) ++p;  // p = first right frame at or after tl[i]
+    int64_t pick; double gap;
+    if (p == 0) { pick = 0; gap = std::fabs(tl[i] - tr[0]); }
+    else {
+      int64_t q = p - 1;
+      while (q > 0 && tr[q - 1] == tr[q]) --q;  // lowest index among equal timestamps
+      double a = std::fabs(tl[i] - tr[q]);
+      if (p < nr) {
+        double b = std::fabs(tl[i] - tr[p]);
+        if (b < a) { pick = p; gap = b; } else { pick = q; gap = a; }  // earlier frame on a tie
+      } else { pick = q; gap = a; }
+    }
+    if (!(gap <= max_dt)) continue;
+    if (pick == g_right) {
+      if (gap < g_gap) { g_left = i; g_gap = gap; }  // the closer left frame keeps it (lowest index on a tie)
+    } else {
+      if (!flush()) return USV_ERR_INVALID_ARG;
+      g_right = pick; g_left = i; g_gap = gap;
+    }
+  }
+  if (!flush()) return USV_ERR_INVALID_ARG;
+  return n;
+}
+
+// ---- streamed matching -------------------------------------------------------------------
+struct Slot {
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  uint8_t *h_l = nullptr, *h_r = nullptr, *d_l = nullptr, *d_r = nullptr;
+  usv_outputs h_out, d_out;
+};
+
+struct usv_stream {
+  usv_ctx* ctx = nullptr;
+  usv_frame_desc hf, df;
+  usv_search_params params;
+  int32_t pairs_per_slot = 0, n_slots = 0;
+  uint32_t mask = 0;
+  int64_t n_win = 0;
+  std::vector<Slot> slots;
+};
+
+extern "C" int usv_stream_destroy(usv_stream* s) {
+  if (!s) return USV_ERR_INVALID_ARG;
+  cudaSetDevice(s->ctx->device);
+  for (Slot& sl : s->slots) {
+    if (sl.st) cudaStreamSynchronize(sl.st);
+    if (sl.h_l) cudaFreeHost(sl.h_l);
+    if (sl.h_r) cudaFreeHost(sl.h_r);
+    if (sl.d_l) cudaFree(sl.d_l);
+    if (sl.d_r) cudaFree(sl.d_r);
+    for (int i = 0; i < 7; ++i) {
+      if (*out_slot(&sl.h_out, i)) cudaFreeHost(*out_slot(&sl.h_out, i));
+      if (*out_slot(&sl.d_out, i)) cudaFree(*out_slot(&sl.d_out, i));
+    }
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.st) cudaStreamDestroy(sl.st);
+  }
+  delete s;
+  return USV_OK;
+}
+
+extern "C" int usv_stream_create(usv_ctx* ctx, const usv_frame_desc* frame, const usv_search_params* params, int32_t pairs_per_slot,
+                                 int32_t n_slots, uint32_t output_mask, usv_stream** out) {
+  if (!ctx || !out) return USV_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (pairs_per_slot <= 0 || n_slots <= 0 || n_slots > 64) return fail(ctx, USV_ERR_INVALID_ARG, "bad slot geometry");
+  int rc = check_common(ctx, frame, params, pairs_per_slot);
+  if (rc) return rc;
+  int32_t nx, ny;
+  if (usv_grid_dims(frame, params, &nx, &ny, nullptr)) return fail(ctx, USV_ERR_INVALID_ARG, "bad geometry");
+  CU(cudaSetDevice(ctx->device));
+  usv_stream* s = new (std::nothrow) usv_stream();
+  if (!s) return fail(ctx, USV_ERR_NOMEM, "out of host memory");
+  s->ctx = ctx; s->params = *params; s->pairs_per_slot = pairs_per_slot; s->n_slots = n_slots; s->mask = output_mask;
+  s->n_win = (int64_t)nx * ny;
+  // pinned staging keeps the frames tightly packed at a 128-byte pitch, the same layout as in HBM,
+  // so each slot needs exactly one cudaMemcpyAsync per camera
+  const int pitch = (frame->width * frame->channels + 127) & ~127;
+  s->hf = *frame; s->hf.row_stride = pitch; s->hf.frame_stride = (int64_t)pitch * frame->height;
+  s->df = s->hf;
+  s->slots.resize(n_slots);
+  const size_t fbytes = (size_t)s->hf.frame_stride * pairs_per_slot;
+  const size_t n_res = (size_t)s->n_win * pairs_per_slot;
+  cudaError_t e = cudaSuccess;
+  for (Slot& sl : s->slots) {
+    memset(&sl.h_out, 0, sizeof(sl.h_out));
+    memset(&sl.d_out, 0, sizeof(sl.d_out));
+    if ((e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) break;
+    if ((e = cudaHostAlloc((void**)&sl.h_l, fbytes, cudaHostAllocDefault)) != cudaSuccess) break;
+    if ((e = cudaHostAlloc((void**)&sl.h_r, fbytes, cudaHostAllocDefault)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&sl.d_l, fbytes)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&sl.d_r, fbytes)) != cudaSuccess) break;
+    memset(sl.h_l, 0, fbytes);
+    memset(sl.h_r, 0, fbytes);
+    for (int i = 0; i < 7 && e == cudaSuccess; ++i) {
+      if (!(output_mask & (1u << i))) continue;
+      if ((e = cudaHostAlloc(out_slot(&sl.h_out, i), kOutElem[i] * n_res, cudaHostAllocDefault)) != cudaSuccess) break;
+      e = cudaMalloc(out_slot(&sl.d_out, i), kOutElem[i] * n_res);
+    }
+    if (e != cudaSuccess) break;
+  }
+  if (e != cudaSuccess) {
+    fail(ctx, USV_ERR_NOMEM, "stream allocation: %s", cudaGetErrorString(e));
+    usv_stream_destroy(s);
+    return USV_ERR_NOMEM;
+  }
+  *out = s;
+  return USV_OK;
+}
+
+extern "C" int usv_stream_slot(usv_stream* s, int32_t slot, uint8_t** h_left, uint8_t** h_right, usv_outputs* h_out) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  if (h_left) *h_left = s->slots[slot].h_l;
+  if (h_right) *h_right = s->slots[slot].h_r;
+  if (h_out) *h_out = s->slots[slot].h_out;
+  return USV_OK;
+}
+
+extern "C" int usv_stream_frame_desc(const usv_stream* s, usv_frame_desc* out) {
+  if (!s || !out) return USV_ERR_INVALID_ARG;
+  *out = s->hf;
+  return USV_OK;
+}
+
+extern "C" int usv_stream_submit(usv_stream* s, int32_t slot, int32_t n_pairs) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  usv_ctx* ctx = s->ctx;
+  if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
+  CU(cudaSetDevice(ctx->device));
+  Slot& sl = s->slots[slot];
+  if (n_pairs > 0) {
+    const size_t fbytes = (size_t)s->hf.frame_stride * n_pairs;
+    CU(cudaMemcpyAsync(sl.d_l, sl.h_l, fbytes, cudaMemcpyHostToDevice, sl.st));
+    CU(cudaMemcpyAsync(sl.d_r, sl.h_r, fbytes, cudaMemcpyHostToDevice, sl.st));
+    int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
+    if (rc) return rc;
+    const size_t n_res = (size_t)s->n_win * n_pairs;
+    for (int i = 0; i < 7; ++i)
+      if (*out_slot(&sl.h_out, i))
+        CU(cudaMemcpyAsync(*out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res, cudaMemcpyDeviceToHost, sl.st));
+  }
+  CU(cudaEventRecord(sl.done, sl.st));
+  return USV_OK;
+}
+
+extern "C" int usv_stream_wait(usv_stream* s, int32_t slot) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  usv_ctx* ctx = s->ctx;
+  CU(cudaEventSynchronize(s->slots[slot].done));
+  return USV_OK;
+}
+
+extern "C" int usv_stream_bytes_per_pair(const usv_stream* s, int64_t* h2d, int64_t* d2h) {
+  if (!s) return USV_ERR_INVALID_ARG;
+  if (h2d) *h2d = 2 * s->hf.frame_stride;
+  int64_t o = 0;
+  for (int i = 0; i < 7; ++i)
+    if (s->mask & (1u << i)) o += (int64_t)kOutElem[i] * s->n_win;
+  if (d2h) *d2h = o;
+  return USV_OK;
+}
