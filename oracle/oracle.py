@@ -30,10 +30,19 @@ _ref = None
 _P = C.POINTER
 
 
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(ORACLE_SO):
+        srcs = [os.path.join(HERE, f) for f in ("block_search_oracle.c", "distance_oracle.c", "Makefile")]
+        srcs.append(os.path.join(HERE, "..", "include", "usv_b200.h"))
+        if _stale(ORACLE_SO, srcs):
             build()
         L = C.CDLL(ORACLE_SO)
         L.usv_oracle_distance.restype = C.c_double

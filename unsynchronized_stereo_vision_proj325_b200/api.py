@@ -111,11 +111,15 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().usv_destroy(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.usv_destroy(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter teardown
+            pass
 
     def __enter__(self):
         return self
@@ -255,9 +259,13 @@ class Stream:
         self.ctx._check(lib().usv_stream_wait(self._h, C.c_int32(slot)), "usv_stream_wait")
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             self.slots = []
-            lib().usv_stream_destroy(self._h)
-            self._h = None
+            _lib.usv_stream_destroy(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter teardown
+            pass

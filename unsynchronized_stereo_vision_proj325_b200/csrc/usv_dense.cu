@@ -1,11 +1,284 @@
-// usv_dense.cu — dense stride-1 sweep kernels (sliding-window formulation).
+// usv_dense.cu — dense stride-1 sweep for sm_100a: sliding-window SAD with a fused
+// argmin + distance epilogue.
+//
+// Algorithm (exact in integers, identical results to the direct form):
+//   h(u, d, v)  = sum_{b<4} |L[v][u+b] - R[v][u-d+b]|           one VABSDIFF4.U8.ACC
+//   V(u, d, y)  = sum_{v in [y, y+th)} h(u, d, v)               kept in a register and slid
+//                                                                down the rows: + new row, - old row
+//   S(x, d, y)  = sum_{k < tw/4} V(x + 4k, d, y)                 SAD of window x vs candidate x-d
+// so a candidate costs ~2 VABSDIFF4 + ~3 integer adds instead of tw*th/4 VABSDIFF4.
+//
+// Mapping. A CTA owns an x-tile (<= 128 px) x a band of BH output rows of one frame
+// pair and walks the disparity range in passes of 32. Its four warps are the four
+// byte phases p = x mod 4 (packed-byte operands must be word aligned, so shared
+// memory holds four byte-shifted copies of the L rows and of the R rows). Inside a
+// warp 8 lanes run along x (4 window positions each) and 4 lanes along d (8
+// disparities each, 4 apart): 32 V accumulators per thread. Window sums need the
+// next lane's first columns: a width-8 shuffle of three prefix sums. The running
+// best of every window lives in shared memory as one packed u32 key
+// (cost << XB | candidate code) so that "smallest cost, then smallest x'"
+// (P/Main.cpp:451: an equal later candidate never replaces) is a single unsigned
+// min whatever the reduction order. After the last pass the CTA decodes its keys and
+// writes Match records / disparity / distance (LUT of the reference's formulas).
+//
+// Pipes (measured on B200, profiles/microbench_r1.jsonl): VABSDIFF4/IADD3 issue at 64
+// lanes/clk/SM on the ALU pipe, IMAD at 64 lanes/clk/SM on the FMA pipe in parallel,
+// VIMNMX at 128. The row-difference subtraction and the key packing are IMADs on
+// purpose, to keep them off the ALU pipe that bounds this kernel.
 #include "usv_common.cuh"
 
 namespace usv {
 
+constexpr int kDenseThreads = 128;
+constexpr int kRB = 8;          // rows per staging block
+constexpr int kLW = 32;         // words per L copy row (128 B)
+constexpr int kRW = 40;         // words per R copy row (160 B)
+constexpr int kRowWords = 4 * kLW + 4 * kRW;  // one ring row: 4 L copies + 4 R copies
+constexpr int kCodeOff = 16;    // candidate code = x0 -/+ d + kCodeOff  (> 0 for every valid candidate)
+
+struct DenseCfg {
+  int stride_px;    // x-tile stride = 4 * (32 - tw/4 + 1)
+  int n_xtiles;
+  int bh;           // output rows per band
+  int n_bands;
+  int nr;           // ring rows (>= th + 2*kRB)
+  int xb;           // bits of the candidate code inside the key
+};
+
+__device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
+// Q = tw / 16 (window = 4*Q packed words).
+template <int DIR, int Q>
+__global__ void __launch_bounds__(kDenseThreads, 3)
+dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  uint32_t* s_ring = smem_u32;                                  // [nr][kRowWords]
+  uint32_t* s_best = smem_u32 + (size_t)cfg.nr * kRowWords;     // [bh][4][32]
+
+  const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;   // p: byte phase of this warp
+  const int ul = lane & 7, dl = lane >> 3;
+  const int tile = blockIdx.x, band = blockIdx.y, pair = blockIdx.z;
+  const int X0 = tile * cfg.stride_px;
+  const int y0 = band * cfg.bh;
+  const int bh = min(cfg.bh, J.nyc - y0);
+  const int th = J.th;
+  const int rows_in = bh + th - 1;
+  const int x0 = X0 + p + 16 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i)
+  const uint32_t* Lg = reinterpret_cast<const uint32_t*>(J.left + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
+  const uint32_t* Rg = reinterpret_cast<const uint32_t*>(J.right + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
+  const int row_words = J.row_stride >> 2;
+  const int xb = cfg.xb;
+  const uint32_t key_scale = 1u << xb;
+
+  for (int i = tid; i < bh * 128; i += kDenseThreads) s_best[i] = 0xffffffffu;
+
+  // disparity range this tile can use
+  const int x_hi = min(X0 + cfg.stride_px - 1, J.nxc - 1);
+  int d_lo, d_hi;
+  if (DIR < 0) { d_lo = max(J.dmin, X0 - (J.nxc - 1)); d_hi = min(J.dmax, x_hi); }
+  else { d_lo = max(J.dmin, -x_hi); d_hi = min(J.dmax, J.nxc - 1 - X0); }
+  // warp p, lane dl covers d = D0 + 4j + (p - dl) [LeftCam] / D0 + 4j + (dl - p) [RightCam], j < 8:
+  // every warp sees 32 consecutive d starting in [D0 - 3, D0]; the shortest reach is D0 + 28.
+  const int n_pass = d_hi >= d_lo ? (d_hi - d_lo + 3) / 32 + 1 : 0;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int D0 = d_lo + 32 * pass;
+    // d of (this lane, j = 0); d_j = dbase + 4j
+    const int dbase = D0 + (DIR < 0 ? (p - dl) : (dl - p));
+    // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
+    const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
+
+    // validity mask of the 32 (i, j) elements; code registers
+    uint32_t vm = 0;
+    uint32_t code[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int d = dbase + 4 * j;
+      code[j] = (uint32_t)((DIR < 0 ? x0 - d : x0 + d) + kCodeOff);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x0 + 4 * i;
+        const int xr = DIR < 0 ? x - d : x + d;
+        const bool ok = (d >= J.dmin && d <= J.dmax && xr >= 0 && xr <= J.nxc - 1) || x > J.nxc - 1;
+        vm |= (ok ? 1u : 0u) << (i * 8 + j);
+      }
+    }
+    const bool interior = __all_sync(0xffffffffu, vm == 0xffffffffu);
+
+    uint32_t V[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) V[i][j] = 0;
+
+    // ---- software staging of a block of rows into the ring (4 + 4 byte-shifted copies)
+    auto stage = [&](int row_begin) {
+      const int nrows = min(kRB, rows_in - row_begin);
+      if (nrows <= 0) return;
+      for (int idx = tid; idx < nrows * kRowWords; idx += kDenseThreads) {
+        const int r = idx / kRowWords, rem = idx - r * kRowWords;
+        const int row = row_begin + r;
+        int o;  // byte offset of this word inside the global row
+        const uint32_t* G;
+        if (rem < 4 * kLW) { const int c = rem / kLW, w = rem - c * kLW; o = X0 + c + 4 * w; G = Lg; }
+        else { const int rr = rem - 4 * kLW; const int c = rr / kRW, w = rr - c * kRW; o = XR0 + c + 4 * w; G = Rg; }
+        G += (long long)row * row_words;
+        const int g = o >> 2;  // floor for negative offsets too
+        const int g0 = min(max(g, 0), row_words - 1), g1 = min(max(g + 1, 0), row_words - 1);
+        const uint32_t v = __funnelshift_r(__ldg(G + g0), __ldg(G + g1), (o & 3) * 8);
+        s_ring[(size_t)(row % cfg.nr) * kRowWords + rem] = v;
+      }
+    };
+
+    __syncthreads();  // previous pass done with the ring; s_best init visible
+    stage(0);
+    __syncthreads();
+
+    const int n_blk = (rows_in + kRB - 1) / kRB;
+    for (int blk = 0; blk < n_blk; ++blk) {
+      stage((blk + 1) * kRB);  // ring depth >= th + 2*kRB keeps every row still needed by this block intact
+      const int r_end = min(rows_in, (blk + 1) * kRB);
+      for (int row = blk * kRB; row < r_end; ++row) {
+        // ---- new row
+        {
+          const uint32_t* base = s_ring + (size_t)(row % cfg.nr) * kRowWords;
+          const uint4 l4 = *reinterpret_cast<const uint4*>(base + p * kLW + 4 * ul);
+          const uint4* rp = reinterpret_cast<const uint4*>(base + 4 * kLW + dl * kRW + 4 * ul);
+          const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+          const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
+          const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], V[i][j]);
+        }
+        // ---- old row leaves the window
+        if (row >= th) {
+          const uint32_t* base = s_ring + (size_t)((row - th) % cfg.nr) * kRowWords;
+          const uint4 l4 = *reinterpret_cast<const uint4*>(base + p * kLW + 4 * ul);
+          const uint4* rp = reinterpret_cast<const uint4*>(base + 4 * kLW + dl * kRW + 4 * ul);
+          const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+          const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
+          const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], 0u);
+              V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
+            }
+        }
+        // ---- window sums, keys, running min
+        if (row >= th - 1) {
+          uint32_t best[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t pre1 = V[0][j], pre2 = pre1 + V[1][j], pre3 = pre2 + V[2][j], tot = pre3 + V[3][j];
+            uint32_t T0 = tot;
+#pragma unroll
+            for (int s = 1; s < Q; ++s) T0 += __shfl_down_sync(0xffffffffu, tot, s, 8);
+            const uint32_t h1 = __shfl_down_sync(0xffffffffu, pre1, Q, 8);
+            const uint32_t h2 = __shfl_down_sync(0xffffffffu, pre2, Q, 8);
+            const uint32_t h3 = __shfl_down_sync(0xffffffffu, pre3, Q, 8);
+            uint32_t T[4];
+            T[0] = T0; T[1] = T0 - pre1 + h1; T[2] = T0 - pre2 + h2; T[3] = T0 - pre3 + h3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t key = imad_u32(T[i], key_scale, code[j]);
+              if (!interior && !((vm >> (i * 8 + j)) & 1u)) key = 0xffffffffu;
+              best[i] = min(best[i], key);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 8));
+            best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 16));
+          }
+          if (dl == 0) {
+            uint4* bp = reinterpret_cast<uint4*>(s_best + ((size_t)(row - (th - 1)) * 4 + p) * 32 + 4 * ul);
+            uint4 b = *bp;
+            b.x = min(b.x, best[0]); b.y = min(b.y, best[1]); b.z = min(b.z, best[2]); b.w = min(b.w, best[3]);
+            *bp = b;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  // ---- fused epilogue: key -> (cost, x') -> Match / disparity / distance
+  const int n_pos = 32 - 4 * Q + 1;  // valid window positions per phase in a tile
+  const int span = min(cfg.stride_px, J.nxc - X0);
+  const uint32_t code_mask = key_scale - 1;
+  for (int idx = tid; idx < bh * span; idx += kDenseThreads) {
+    const int yy = idx / span, xo = idx - yy * span;
+    const int pp = xo & 3, a = xo >> 2;
+    if (a >= n_pos) continue;
+    const uint32_t key = s_best[((size_t)yy * 4 + pp) * 32 + a];
+    const int x = X0 + xo, y = y0 + yy;
+    const long long w = (long long)y * J.nx + x;
+    const long long g = (long long)pair * J.n_templates + w;
+    if (key == 0xffffffffu) {
+      write_result(J, g, (uint32_t)w, x, y, -1, 0xffffffffu, 0.0, __longlong_as_double(0x7ff0000000000000ll));
+    } else {
+      const uint32_t raw = key >> xb;
+      const int c = (int)(key & code_mask) - kCodeOff;  // = x0 -/+ d of the owning thread column 0
+      const int xr = c + 4 * (a & 3);
+      write_result(J, g, (uint32_t)w, x, y, xr, raw, 0.0, normalised_cost(raw, USV_COST_SAD, J.n_elems));
+    }
+  }
+}
+
+static int ceil_log2(long long v) {
+  int b = 0;
+  while ((1ll << b) < v) ++b;
+  return b;
+}
+
 cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches) {
-  (void)J; (void)n_pairs; (void)st; (void)kernel_name; (void)n_launches;
-  return cudaErrorNotSupported;
+  // coverage of the sliding-window kernels; everything else runs on the direct-form kernel
+  if (J.tx || J.channels != 1 || J.sx != 1 || J.sy != 1) return cudaErrorNotSupported;
+  if (J.cost_kind != USV_COST_SAD) return cudaErrorNotSupported;
+  if (J.tw % 16 != 0 || J.tw > 32 || J.th > 64) return cudaErrorNotSupported;
+  if (J.out.score) { /* score is 0 for integer kinds; write_result handles it */ }
+  const int q = J.tw / 16;
+  DenseCfg cfg;
+  cfg.stride_px = 4 * (32 - 4 * q + 1);
+  cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
+  cfg.xb = ceil_log2((long long)J.nxc + kCodeOff + 16 + 1);
+  const long long smax = 255ll * J.n_elems;
+  if (ceil_log2(smax + 1) + cfg.xb > 32) return cudaErrorNotSupported;
+  if (((smax << cfg.xb) | ((1ll << cfg.xb) - 1)) >= 0xffffffffll) return cudaErrorNotSupported;  // ~0 is the "no candidate" key
+  cfg.nr = J.th + 2 * kRB;
+  // bands: as tall as shared memory allows (amortises the th-1 warm-up rows), but enough CTAs to fill 148 SMs
+  const int smem_budget = 72 * 1024;  // 3 CTAs / SM
+  int bh_max = (smem_budget - cfg.nr * kRowWords * 4) / 512;
+  if (bh_max < 8) return cudaErrorNotSupported;
+  int n_bands = (J.nyc + bh_max - 1) / bh_max;
+  while ((long long)n_bands * cfg.n_xtiles * n_pairs < 148 * 3 && n_bands < (J.nyc + 15) / 16) ++n_bands;
+  cfg.bh = (J.nyc + n_bands - 1) / n_bands;
+  cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
+  const size_t smem = (size_t)cfg.nr * kRowWords * 4 + (size_t)cfg.bh * 512;
+  dim3 grid(cfg.n_xtiles, cfg.n_bands, n_pairs), block(kDenseThreads);
+#define USV_DENSE_LAUNCH(D, QQ)                                                                           \
+  {                                                                                                       \
+    auto kfn = dense_sad_argmin_kernel<D, QQ>;                                                            \
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    if (e != cudaSuccess) return e;                                                                       \
+    kfn<<<grid, block, smem, st>>>(J, cfg, 0xffffffffu);                                                  \
+  }
+  if (J.camera_side == USV_LEFT_CAM) { if (q == 1) USV_DENSE_LAUNCH(-1, 1) else USV_DENSE_LAUNCH(-1, 2) }
+  else { if (q == 1) USV_DENSE_LAUNCH(1, 1) else USV_DENSE_LAUNCH(1, 2) }
+#undef USV_DENSE_LAUNCH
+  *kernel_name = "dense_sad_argmin_kernel";
+  *n_launches = 1;
+  return cudaGetLastError();
 }
 
 }  // namespace usv

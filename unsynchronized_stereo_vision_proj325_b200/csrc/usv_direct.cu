@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kDirectThreads)
 block_cost_argmin_direct(const DevJob J, int tmpl_pitch_words, int strip_pitch_words, int rows_per_chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_tmpl = reinterpret_cast<uint32_t*>(smem_raw);                 // [th][tmpl_pitch_words]
-  uint32_t* s_strip = s_tmpl + (size_t)J.th * tmpl_pitch_words;             // [rows_per_chunk][strip_pitch_words]
+  uint32_t* s_strip = s_tmpl + (((size_t)J.th * tmpl_pitch_words + 3) & ~(size_t)3);  // [rows_per_chunk][strip_pitch_words], 16-B aligned
   __shared__ unsigned long long s_red[kDirectThreads / 32];
   __shared__ double s_redv[kDirectThreads / 32];
   __shared__ unsigned s_redj[kDirectThreads / 32];
@@ -253,6 +253,8 @@ block_cost_argmin_direct(const DevJob J, int tmpl_pitch_words, int strip_pitch_w
 template <int KIND>
 static cudaError_t launch_direct_c(const DevJob& J, int n_pairs, cudaStream_t st) {
   const int nw = (J.row_bytes + 3) / 4;
+  // odd pitch in words avoids bank conflicts; the whole template area is padded to 16 B so the
+  // strip area that follows it stays cp.async (16-byte) aligned
   const int tmpl_pitch_words = nw + 1;
   // widest strip a pass can need: (chunk candidates + template) bytes + alignment slack
   int max_c = J.nxc < kChunkCands ? J.nxc : kChunkCands;
@@ -265,7 +267,7 @@ static cudaError_t launch_direct_c(const DevJob& J, int n_pairs, cudaStream_t st
   if (rows > J.th) rows = J.th;
   size_t strip_area = (size_t)rows * strip_pitch_words * 4;
   if (strip_area < (size_t)tmpl_stage_bytes) strip_area = tmpl_stage_bytes;
-  size_t smem = (size_t)J.th * tmpl_pitch_words * 4 + strip_area;
+  size_t smem = ((((size_t)J.th * tmpl_pitch_words + 3) & ~(size_t)3) * 4) + strip_area;
   smem = (smem + 15) & ~(size_t)15;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid(J.n_templates, n_pairs), block(kDirectThreads);
