@@ -51,6 +51,158 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
   return d;
 }
 
+// One pass of a warp over all rows of the band for 32 disparities.
+// MASKED = false: every (i, j) element of every lane is a valid candidate -> 8 code registers.
+// MASKED = true : per-element codes; an invalid candidate carries bit 31 in its code and can
+//                 never beat a valid one (valid keys stay below 2^31, checked on the host).
+template <int DIR, int Q, bool MASKED>
+__device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
+                                           const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
+                                           const int XR0, const int x0, const int dbase, const int rows_in,
+                                           const uint32_t minus_one) {
+  const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
+  const int ul = lane & 7, dl = lane >> 3;
+  const int th = J.th, nr = cfg.nr;
+  const int row_words = J.row_stride >> 2;
+  const uint32_t key_scale = 1u << cfg.xb;
+
+  constexpr int NC = MASKED ? 4 : 1;
+  uint32_t code[NC][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = dbase + 4 * j;
+    const uint32_t c = (uint32_t)((DIR < 0 ? x0 - d : x0 + d) + kCodeOff);
+    if (!MASKED) { code[0][j] = c; }
+    else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x0 + 4 * i;
+        const int xr = DIR < 0 ? x - d : x + d;
+        const bool ok = d >= J.dmin && d <= J.dmax && xr >= 0 && xr <= J.nxc - 1;
+        code[i][j] = ok ? c : 0x80000000u;  // T*scale < 2^31, so the sum cannot wrap
+      }
+    }
+  }
+
+  // ---- staging roles: thread t < 32 stages L word t, 32 <= t < 72 stages R word t - 32, for all
+  // four byte-shifted copies (one pair of aligned global words -> 4 funnel shifts -> 4 STS)
+  const bool stager = tid < 72;
+  const bool st_left = tid < 32;
+  const int st_w = st_left ? tid : tid - 32;
+  const int st_kw = st_left ? kLW : kRW;
+  const int st_off = (st_left ? 0 : 4 * kLW) + st_w;
+  const uint32_t* st_g = st_left ? Lg : Rg;
+  int g0, g1;
+  {
+    const int gb = ((st_left ? X0 : XR0) >> 2) + st_w;  // X0, XR0 are multiples of 4
+    g0 = min(max(gb, 0), row_words - 1);
+    g1 = min(max(gb + 1, 0), row_words - 1);
+  }
+  auto stage = [&](int row_begin) {
+    if (!stager) return;
+    const int nrows = min(kRB, rows_in - row_begin);
+    if (nrows <= 0) return;
+    uint32_t a[kRB], b[kRB];
+    const uint32_t* gp = st_g + (long long)row_begin * row_words;
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) {
+      if (r < nrows) { a[r] = __ldg(gp + g0); b[r] = __ldg(gp + g1); gp += row_words; }
+    }
+    int slot = row_begin % nr;
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) {
+      if (r < nrows) {
+        uint32_t* dst = s_ring + (size_t)slot * kRowWords + st_off;
+        dst[0] = a[r];
+        dst[st_kw] = __funnelshift_r(a[r], b[r], 8);
+        dst[2 * st_kw] = __funnelshift_r(a[r], b[r], 16);
+        dst[3 * st_kw] = __funnelshift_r(a[r], b[r], 24);
+        slot = slot + 1 == nr ? 0 : slot + 1;
+      }
+    }
+  };
+
+  uint32_t V[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) V[i][j] = 0;
+
+  __syncthreads();  // previous pass done with the ring; s_best init visible
+  stage(0);
+  __syncthreads();
+
+  const uint32_t* my_l = s_ring + p * kLW + 4 * ul;
+  const uint32_t* my_r = s_ring + 4 * kLW + dl * kRW + 4 * ul;
+  int slot_new = 0, slot_old = 0;
+  const int n_blk = (rows_in + kRB - 1) / kRB;
+  for (int blk = 0; blk < n_blk; ++blk) {
+    stage((blk + 1) * kRB);  // ring depth >= th + 2*kRB keeps every row this block still needs intact
+    const int r_end = min(rows_in, (blk + 1) * kRB);
+    for (int row = blk * kRB; row < r_end; ++row) {
+      // ---- new row enters the window
+      {
+        const uint4 l4 = *reinterpret_cast<const uint4*>(my_l + (size_t)slot_new * kRowWords);
+        const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_new * kRowWords);
+        const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
+        const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], V[i][j]);
+        slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
+      }
+      // ---- old row leaves the window
+      if (row >= th) {
+        const uint4 l4 = *reinterpret_cast<const uint4*>(my_l + (size_t)slot_old * kRowWords);
+        const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_old * kRowWords);
+        const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
+        const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], 0u);
+            V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
+          }
+        slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
+      }
+      // ---- window sums, keys, running min
+      if (row >= th - 1) {
+        uint32_t best[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t pre1 = V[0][j], pre2 = pre1 + V[1][j], pre3 = pre2 + V[2][j], tot = pre3 + V[3][j];
+          uint32_t T0 = tot;
+#pragma unroll
+          for (int s = 1; s < Q; ++s) T0 += __shfl_down_sync(0xffffffffu, tot, s, 8);
+          const uint32_t h1 = __shfl_down_sync(0xffffffffu, pre1, Q, 8);
+          const uint32_t h2 = __shfl_down_sync(0xffffffffu, pre2, Q, 8);
+          const uint32_t h3 = __shfl_down_sync(0xffffffffu, pre3, Q, 8);
+          uint32_t T[4];
+          T[0] = T0; T[1] = T0 - pre1 + h1; T[2] = T0 - pre2 + h2; T[3] = T0 - pre3 + h3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) best[i] = min(best[i], imad_u32(T[i], key_scale, code[MASKED ? i : 0][j]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 8));
+          best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 16));
+        }
+        if (dl == 0) {
+          uint4* bp = reinterpret_cast<uint4*>(s_best + ((size_t)(row - (th - 1)) * 4 + p) * 32 + 4 * ul);
+          uint4 b = *bp;
+          b.x = min(b.x, best[0]); b.y = min(b.y, best[1]); b.z = min(b.z, best[2]); b.w = min(b.w, best[3]);
+          *bp = b;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
 // Q = tw / 16 (window = 4*Q packed words).
 template <int DIR, int Q>
@@ -66,14 +218,11 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   const int X0 = tile * cfg.stride_px;
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
-  const int th = J.th;
-  const int rows_in = bh + th - 1;
+  const int rows_in = bh + J.th - 1;
   const int x0 = X0 + p + 16 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i)
   const uint32_t* Lg = reinterpret_cast<const uint32_t*>(J.left + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
   const uint32_t* Rg = reinterpret_cast<const uint32_t*>(J.right + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
-  const int row_words = J.row_stride >> 2;
   const int xb = cfg.xb;
-  const uint32_t key_scale = 1u << xb;
 
   for (int i = tid; i < bh * 128; i += kDenseThreads) s_best[i] = 0xffffffffu;
 
@@ -82,140 +231,38 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   int d_lo, d_hi;
   if (DIR < 0) { d_lo = max(J.dmin, X0 - (J.nxc - 1)); d_hi = min(J.dmax, x_hi); }
   else { d_lo = max(J.dmin, -x_hi); d_hi = min(J.dmax, J.nxc - 1 - X0); }
+  d_lo = d_lo & ~3;  // floor to a multiple of 4 (also for negatives): keeps the R copies word aligned
   // warp p, lane dl covers d = D0 + 4j + (p - dl) [LeftCam] / D0 + 4j + (dl - p) [RightCam], j < 8:
   // every warp sees 32 consecutive d starting in [D0 - 3, D0]; the shortest reach is D0 + 28.
   const int n_pass = d_hi >= d_lo ? (d_hi - d_lo + 3) / 32 + 1 : 0;
 
   for (int pass = 0; pass < n_pass; ++pass) {
     const int D0 = d_lo + 32 * pass;
-    // d of (this lane, j = 0); d_j = dbase + 4j
-    const int dbase = D0 + (DIR < 0 ? (p - dl) : (dl - p));
+    const int dbase = D0 + (DIR < 0 ? (p - dl) : (dl - p));  // d of (this lane, j = 0); d_j = dbase + 4j
     // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
-
-    // validity mask of the 32 (i, j) elements; code registers
-    uint32_t vm = 0;
-    uint32_t code[8];
+    // is every element of every lane of this warp a valid candidate? (windows beyond the frame do not count)
+    bool all_ok = true;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int d = dbase + 4 * j;
-      code[j] = (uint32_t)((DIR < 0 ? x0 - d : x0 + d) + kCodeOff);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int x = x0 + 4 * i;
         const int xr = DIR < 0 ? x - d : x + d;
-        const bool ok = (d >= J.dmin && d <= J.dmax && xr >= 0 && xr <= J.nxc - 1) || x > J.nxc - 1;
-        vm |= (ok ? 1u : 0u) << (i * 8 + j);
+        all_ok = all_ok && ((d >= J.dmin && d <= J.dmax && xr >= 0 && xr <= J.nxc - 1) || x > J.nxc - 1);
       }
     }
-    const bool interior = __all_sync(0xffffffffu, vm == 0xffffffffu);
-
-    uint32_t V[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) V[i][j] = 0;
-
-    // ---- software staging of a block of rows into the ring (4 + 4 byte-shifted copies)
-    auto stage = [&](int row_begin) {
-      const int nrows = min(kRB, rows_in - row_begin);
-      if (nrows <= 0) return;
-      for (int idx = tid; idx < nrows * kRowWords; idx += kDenseThreads) {
-        const int r = idx / kRowWords, rem = idx - r * kRowWords;
-        const int row = row_begin + r;
-        int o;  // byte offset of this word inside the global row
-        const uint32_t* G;
-        if (rem < 4 * kLW) { const int c = rem / kLW, w = rem - c * kLW; o = X0 + c + 4 * w; G = Lg; }
-        else { const int rr = rem - 4 * kLW; const int c = rr / kRW, w = rr - c * kRW; o = XR0 + c + 4 * w; G = Rg; }
-        G += (long long)row * row_words;
-        const int g = o >> 2;  // floor for negative offsets too
-        const int g0 = min(max(g, 0), row_words - 1), g1 = min(max(g + 1, 0), row_words - 1);
-        const uint32_t v = __funnelshift_r(__ldg(G + g0), __ldg(G + g1), (o & 3) * 8);
-        s_ring[(size_t)(row % cfg.nr) * kRowWords + rem] = v;
-      }
-    };
-
-    __syncthreads();  // previous pass done with the ring; s_best init visible
-    stage(0);
-    __syncthreads();
-
-    const int n_blk = (rows_in + kRB - 1) / kRB;
-    for (int blk = 0; blk < n_blk; ++blk) {
-      stage((blk + 1) * kRB);  // ring depth >= th + 2*kRB keeps every row still needed by this block intact
-      const int r_end = min(rows_in, (blk + 1) * kRB);
-      for (int row = blk * kRB; row < r_end; ++row) {
-        // ---- new row
-        {
-          const uint32_t* base = s_ring + (size_t)(row % cfg.nr) * kRowWords;
-          const uint4 l4 = *reinterpret_cast<const uint4*>(base + p * kLW + 4 * ul);
-          const uint4* rp = reinterpret_cast<const uint4*>(base + 4 * kLW + dl * kRW + 4 * ul);
-          const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-          const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
-          const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], V[i][j]);
-        }
-        // ---- old row leaves the window
-        if (row >= th) {
-          const uint32_t* base = s_ring + (size_t)((row - th) % cfg.nr) * kRowWords;
-          const uint4 l4 = *reinterpret_cast<const uint4*>(base + p * kLW + 4 * ul);
-          const uint4* rp = reinterpret_cast<const uint4*>(base + 4 * kLW + dl * kRW + 4 * ul);
-          const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-          const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
-          const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], 0u);
-              V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
-            }
-        }
-        // ---- window sums, keys, running min
-        if (row >= th - 1) {
-          uint32_t best[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t pre1 = V[0][j], pre2 = pre1 + V[1][j], pre3 = pre2 + V[2][j], tot = pre3 + V[3][j];
-            uint32_t T0 = tot;
-#pragma unroll
-            for (int s = 1; s < Q; ++s) T0 += __shfl_down_sync(0xffffffffu, tot, s, 8);
-            const uint32_t h1 = __shfl_down_sync(0xffffffffu, pre1, Q, 8);
-            const uint32_t h2 = __shfl_down_sync(0xffffffffu, pre2, Q, 8);
-            const uint32_t h3 = __shfl_down_sync(0xffffffffu, pre3, Q, 8);
-            uint32_t T[4];
-            T[0] = T0; T[1] = T0 - pre1 + h1; T[2] = T0 - pre2 + h2; T[3] = T0 - pre3 + h3;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t key = imad_u32(T[i], key_scale, code[j]);
-              if (!interior && !((vm >> (i * 8 + j)) & 1u)) key = 0xffffffffu;
-              best[i] = min(best[i], key);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 8));
-            best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 16));
-          }
-          if (dl == 0) {
-            uint4* bp = reinterpret_cast<uint4*>(s_best + ((size_t)(row - (th - 1)) * 4 + p) * 32 + 4 * ul);
-            uint4 b = *bp;
-            b.x = min(b.x, best[0]); b.y = min(b.y, best[1]); b.z = min(b.z, best[2]); b.w = min(b.w, best[3]);
-            *bp = b;
-          }
-        }
-      }
-      __syncthreads();
-    }
+    // the choice must be CTA-uniform in control flow (both variants contain the same barriers), warp-uniform in data
+    if (__all_sync(0xffffffffu, all_ok)) dense_pass<DIR, Q, false>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
+    else dense_pass<DIR, Q, true>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
   }
   __syncthreads();
 
   // ---- fused epilogue: key -> (cost, x') -> Match / disparity / distance
   const int n_pos = 32 - 4 * Q + 1;  // valid window positions per phase in a tile
   const int span = min(cfg.stride_px, J.nxc - X0);
-  const uint32_t code_mask = key_scale - 1;
+  const uint32_t code_mask = (1u << xb) - 1;
   for (int idx = tid; idx < bh * span; idx += kDenseThreads) {
     const int yy = idx / span, xo = idx - yy * span;
     const int pp = xo & 3, a = xo >> 2;
@@ -224,7 +271,7 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     const int x = X0 + xo, y = y0 + yy;
     const long long w = (long long)y * J.nx + x;
     const long long g = (long long)pair * J.n_templates + w;
-    if (key == 0xffffffffu) {
+    if (key & 0x80000000u) {  // untouched (~0) or only invalid candidates
       write_result(J, g, (uint32_t)w, x, y, -1, 0xffffffffu, 0.0, __longlong_as_double(0x7ff0000000000000ll));
     } else {
       const uint32_t raw = key >> xb;
@@ -253,8 +300,7 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
   cfg.xb = ceil_log2((long long)J.nxc + kCodeOff + 16 + 1);
   const long long smax = 255ll * J.n_elems;
-  if (ceil_log2(smax + 1) + cfg.xb > 32) return cudaErrorNotSupported;
-  if (((smax << cfg.xb) | ((1ll << cfg.xb) - 1)) >= 0xffffffffll) return cudaErrorNotSupported;  // ~0 is the "no candidate" key
+  if (ceil_log2(smax + 1) + cfg.xb > 31) return cudaErrorNotSupported;  // bit 31 marks invalid candidates
   cfg.nr = J.th + 2 * kRB;
   // bands: as tall as shared memory allows (amortises the th-1 warm-up rows), but enough CTAs to fill 148 SMs
   const int smem_budget = 72 * 1024;  // 3 CTAs / SM
