@@ -189,6 +189,13 @@ int usv_coordinate_position(usv_ctx *ctx, int32_t camera_side,
                             const double *h_dist, const float *h_xy, int64_t n,
                             double *h_xyz);
 
+/* ---- measurement aid: sustained issue rate (thread-instructions / s) of
+ * VABSDIFF4.U8.ACC (which = 0) or IDP.4A.U8.U8 (which = 1) on every SM, from a
+ * register-only loop timed with CUDA events for about target_ms. bench.py uses
+ * it as the integer-ALU roofline denominator of the same run. */
+int usv_probe_issue_rate(usv_ctx *ctx, int32_t which, double target_ms,
+                         double *lane_inst_per_s);
+
 /* ---- unsynchronized capture replacement (pure host) ---------------------- */
 /* Nearest-timestamp pairing of two ascending timestamp lists (seconds):
  * each left frame takes the right frame with the smallest |tL - tR|
@@ -220,6 +227,12 @@ int usv_stream_slot(usv_stream *s, int32_t slot, uint8_t **h_left,
 int usv_stream_frame_desc(const usv_stream *s, usv_frame_desc *out);
 /* Enqueue H2D + kernels + D2H for the first n_pairs of the slot. */
 int usv_stream_submit(usv_stream *s, int32_t slot, int32_t n_pairs);
+/* Same, but the frames come from the caller's own host buffers (pinned for a
+ * truly asynchronous copy) laid out per `host_frame`; results still land in the
+ * slot's pinned output arrays. */
+int usv_stream_submit_from(usv_stream *s, int32_t slot, const uint8_t *h_left,
+                           const uint8_t *h_right,
+                           const usv_frame_desc *host_frame, int32_t n_pairs);
 /* Block until the slot's D2H has landed. */
 int usv_stream_wait(usv_stream *s, int32_t slot);
 /* Bytes moved per submitted pair (for the bench's e2e accounting). */

@@ -21,8 +21,8 @@ EXPORTS = (
     "usv_grid_dims", "usv_match_dense_device", "usv_match_dense_host", "usv_match_templates_device",
     "usv_match_templates_host", "usv_disparity_to_distance", "usv_moving_object_distance",
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
-    "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_wait",
-    "usv_stream_bytes_per_pair",
+    "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_wait",
+    "usv_stream_bytes_per_pair", "usv_probe_issue_rate",
 )
 
 
@@ -208,6 +208,12 @@ class Context:
                                                   C.c_int64(len(dist)), _ptr(out)), "usv_coordinate_position")
         return out
 
+    def probe_issue_rate(self, which=0, target_ms=20.0):
+        """Sustained thread-instructions/s of VABSDIFF4.U8.ACC (0) / IDP.4A (1): the ALU roofline denominator."""
+        r = C.c_double()
+        self._check(lib().usv_probe_issue_rate(self._h, C.c_int32(which), C.c_double(target_ms), C.byref(r)), "usv_probe_issue_rate")
+        return r.value
+
     def stream(self, frame, params, pairs_per_slot, n_slots=3, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST):
         return Stream(self, frame, params, pairs_per_slot, n_slots, mask)
 
@@ -254,6 +260,13 @@ class Stream:
     def submit(self, slot, n_pairs=None):
         n = self.pairs_per_slot if n_pairs is None else n_pairs
         self.ctx._check(lib().usv_stream_submit(self._h, C.c_int32(slot), C.c_int32(n)), "usv_stream_submit")
+
+    def submit_from(self, slot, left, right, n_pairs=None):
+        """Enqueue from caller-owned host arrays [n, H, W(, C)] (pinned for async copies)."""
+        f = _abi.frame_desc_for(left)
+        n = left.shape[0] if n_pairs is None else n_pairs
+        self.ctx._check(lib().usv_stream_submit_from(self._h, C.c_int32(slot), _ptr(left), _ptr(right), C.byref(f), C.c_int32(n)),
+                        "usv_stream_submit_from")
 
     def wait(self, slot):
         self.ctx._check(lib().usv_stream_wait(self._h, C.c_int32(slot)), "usv_stream_wait")

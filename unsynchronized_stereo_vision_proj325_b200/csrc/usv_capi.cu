@@ -17,6 +17,7 @@ namespace usv {
 cudaError_t launch_direct(const DevJob& J, int n_pairs, cudaStream_t st);
 // returns cudaErrorNotSupported when the dense kernels do not cover the job
 cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches);
+cudaError_t run_issue_probe(int which, int sms, double target_ms, double* lane_inst_per_s, uint32_t* d_scratch, cudaStream_t st);
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
 cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
 cudaError_t launch_moving_object_distance(int camera_side, long long t_this, const float* this_xy, int n_this, const float* other_xy,
@@ -441,6 +442,20 @@ extern "C" int usv_coordinate_position(usv_ctx* ctx, int32_t camera_side, const 
   return USV_OK;
 }
 
+// ---- roofline denominator: sustained issue rate of the packed-byte integer instruction ----
+extern "C" int usv_probe_issue_rate(usv_ctx* ctx, int32_t which, double target_ms, double* lane_inst_per_s) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (!lane_inst_per_s || which < 0 || which > 1 || !(target_ms > 0)) return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, ctx->device));
+  int rc = grow(ctx, ctx->misc[7], 64);
+  if (rc) return rc;
+  CU(usv::run_issue_probe(which, prop.multiProcessorCount, target_ms, lane_inst_per_s, (uint32_t*)ctx->misc[7].p, ctx->stream));
+  ctx->launches += 3;
+  return USV_OK;
+}
+
 // ---- nearest-timestamp pairing (pure host, O(nL + nR)) ---------------------------------
 extern "C" int64_t usv_pair_nearest(const double* tl, int64_t nl, const double* tr, int64_t nr, double max_dt, int32_t* out_l,
                                     int32_t* out_r, int64_t cap) {
@@ -596,6 +611,44 @@ extern "C" int usv_stream_submit(usv_stream* s, int32_t slot, int32_t n_pairs) {
     const size_t fbytes = (size_t)s->hf.frame_stride * n_pairs;
     CU(cudaMemcpyAsync(sl.d_l, sl.h_l, fbytes, cudaMemcpyHostToDevice, sl.st));
     CU(cudaMemcpyAsync(sl.d_r, sl.h_r, fbytes, cudaMemcpyHostToDevice, sl.st));
+    int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
+    if (rc) return rc;
+    const size_t n_res = (size_t)s->n_win * n_pairs;
+    for (int i = 0; i < 7; ++i)
+      if (*out_slot(&sl.h_out, i))
+        CU(cudaMemcpyAsync(*out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res, cudaMemcpyDeviceToHost, sl.st));
+  }
+  CU(cudaEventRecord(sl.done, sl.st));
+  return USV_OK;
+}
+
+extern "C" int usv_stream_submit_from(usv_stream* s, int32_t slot, const uint8_t* h_left, const uint8_t* h_right,
+                                      const usv_frame_desc* hf, int32_t n_pairs) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  usv_ctx* ctx = s->ctx;
+  if (!h_left || !h_right || !hf) return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
+  if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
+  if (hf->width != s->hf.width || hf->height != s->hf.height || hf->channels != s->hf.channels ||
+      hf->row_stride < hf->width * hf->channels)
+    return fail(ctx, USV_ERR_INVALID_ARG, "frame geometry differs from the stream's");
+  CU(cudaSetDevice(ctx->device));
+  Slot& sl = s->slots[slot];
+  if (n_pairs > 0) {
+    const int row_bytes = hf->width * hf->channels;
+    const uint8_t* src[2] = {h_left, h_right};
+    uint8_t* dst[2] = {sl.d_l, sl.d_r};
+    for (int k = 0; k < 2; ++k) {
+      if (hf->row_stride == s->df.row_stride && hf->frame_stride == s->df.frame_stride) {
+        CU(cudaMemcpyAsync(dst[k], src[k], (size_t)s->df.frame_stride * n_pairs, cudaMemcpyHostToDevice, sl.st));
+      } else if (n_pairs == 1 || hf->frame_stride == (int64_t)hf->row_stride * hf->height) {
+        CU(cudaMemcpy2DAsync(dst[k], s->df.row_stride, src[k], hf->row_stride, row_bytes, (size_t)hf->height * n_pairs,
+                             cudaMemcpyHostToDevice, sl.st));
+      } else {
+        for (int i = 0; i < n_pairs; ++i)
+          CU(cudaMemcpy2DAsync(dst[k] + (size_t)i * s->df.frame_stride, s->df.row_stride, src[k] + (size_t)i * hf->frame_stride,
+                               hf->row_stride, row_bytes, hf->height, cudaMemcpyHostToDevice, sl.st));
+      }
+    }
     int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
     if (rc) return rc;
     const size_t n_res = (size_t)s->n_win * n_pairs;
