@@ -8,33 +8,34 @@
 //   S(x, d, y)  = sum_{k < tw/4} V(x + 4k, d, y)                 SAD of window x vs candidate x-d
 // so a candidate costs ~2 VABSDIFF4 + ~3 integer adds instead of tw*th/4 VABSDIFF4.
 //
-// Mapping. A CTA owns an x-tile (<= 128 px) x a band of BH output rows of one frame
-// pair and walks the disparity range in passes of 32. Its four warps are the four
-// byte phases p = x mod 4 (packed-byte operands must be word aligned, so shared
-// memory holds four byte-shifted copies of the L rows and of the R rows). Inside a
-// warp 8 lanes run along x (4 window positions each) and 4 lanes along d (8
-// disparities each, 4 apart): 32 V accumulators per thread. Window sums need the
-// next lane's first columns: a width-8 shuffle of three prefix sums. The running
-// best of every window lives in shared memory as one packed u32 key
-// (cost << XB | candidate code) so that "smallest cost, then smallest x'"
-// (P/Main.cpp:451: an equal later candidate never replaces) is a single unsigned
-// min whatever the reduction order. After the last pass the CTA decodes its keys and
-// writes Match records / disparity / distance (LUT of the reference's formulas).
+// Mapping. A CTA owns an x-tile (116 px for 16-px templates) x a band of output rows of one
+// frame pair and walks the disparity range in passes of 32. Its four warps are the four byte
+// phases p = x mod 4 (packed-byte operands must be word aligned, so the shared-memory ring
+// holds four byte-shifted copies of the L rows and of the R rows). Inside a warp 4 lanes run
+// along x (8 window positions each) and 8 lanes along d (4 disparities each, 4 apart; the lane's
+// R copy q fixes d mod 4): 32 V accumulators per thread. Window sums need the next x-lane's
+// first columns: three width-4 shuffles per disparity. Keys pack (cost << XB | candidate code)
+// so that "smallest cost, then smallest x'" (P/Main.cpp:451: an equal later candidate never
+// replaces) is one unsigned min whatever the reduction order; the key of the next window is
+// slid from the previous one with two IMADs. A reduce-scatter min over the 8 d-lanes leaves
+// each lane with one window of the row, merged into the CTA's running best in shared memory.
+// After the last pass the CTA decodes its keys and writes Match records / disparity / distance
+// (LUT of the reference's formulas, P/Main.cpp:694 and P/DistanceCalculator.cpp:84).
 //
 // Pipes (measured on B200, profiles/microbench_r1.jsonl): VABSDIFF4/IADD3 issue at 64
 // lanes/clk/SM on the ALU pipe, IMAD at 64 lanes/clk/SM on the FMA pipe in parallel,
-// VIMNMX at 128. The row-difference subtraction and the key packing are IMADs on
-// purpose, to keep them off the ALU pipe that bounds this kernel.
+// VIMNMX at 128. The old-row subtraction and the key slide are IMADs on purpose, to keep
+// them off the ALU pipe that bounds this kernel.
 #include "usv_common.cuh"
 
 namespace usv {
 
 constexpr int kDenseThreads = 128;
-constexpr int kRB = 8;          // rows per staging block
+constexpr int kRB = 4;          // rows per staging block
 constexpr int kLW = 32;         // words per L copy row (128 B)
-constexpr int kRW = 40;         // words per R copy row (160 B)
+constexpr int kRW = 44;         // words per R copy row (40 used; 44 keeps the four copies on disjoint banks)
 constexpr int kRowWords = 4 * kLW + 4 * kRW;  // one ring row: 4 L copies + 4 R copies
-constexpr int kCodeOff = 16;    // candidate code = x0 -/+ d + kCodeOff  (> 0 for every valid candidate)
+constexpr int kCodeOff = 32;    // candidate code = x0 -/+ d + kCodeOff: a valid candidate of column i has x0 -/+ d >= -4i >= -28
 
 struct DenseCfg {
   int stride_px;    // x-tile stride = 4 * (32 - tw/4 + 1)
@@ -52,7 +53,9 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 }
 
 // One pass of a warp over all rows of the band for 32 disparities.
-// MASKED = false: every (i, j) element of every lane is a valid candidate -> 8 code registers.
+// Thread tile: 8 window positions (a = 8*ul + i) x 4 disparities (j' = 4*jh + j); lane = 4*dl + ul,
+// dl = 4*jh + q, q = R copy. 32 V accumulators per thread.
+// MASKED = false: every (i, j) element of every lane is a valid candidate -> 4 code registers.
 // MASKED = true : per-element codes; an invalid candidate carries bit 31 in its code and can
 //                 never beat a valid one (valid keys stay below 2^31, checked on the host).
 template <int DIR, int Q, bool MASKED>
@@ -61,21 +64,23 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
                                            const int XR0, const int x0, const int dbase, const int rows_in,
                                            const uint32_t minus_one) {
   const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
-  const int ul = lane & 7, dl = lane >> 3;
+  const int ul = lane & 3, dl = lane >> 2, q = dl & 3, jh = dl >> 2;
   const int th = J.th, nr = cfg.nr;
   const int row_words = J.row_stride >> 2;
   const uint32_t key_scale = 1u << cfg.xb;
+  const uint32_t minus_scale = key_scale * minus_one;  // -(1 << xb), kept opaque so the multiply stays an IMAD
+  constexpr int NW = 4 * Q;  // packed words per window
 
-  constexpr int NC = MASKED ? 4 : 1;
-  uint32_t code[NC][8];
+  constexpr int NC = MASKED ? 8 : 1;
+  uint32_t code[NC][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const int d = dbase + 4 * j;
     const uint32_t c = (uint32_t)((DIR < 0 ? x0 - d : x0 + d) + kCodeOff);
     if (!MASKED) { code[0][j] = c; }
     else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         const int x = x0 + 4 * i;
         const int xr = DIR < 0 ? x - d : x + d;
         const bool ok = d >= J.dmin && d <= J.dmax && xr >= 0 && xr <= J.nxc - 1;
@@ -84,11 +89,11 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
     }
   }
 
-  // ---- staging roles: thread t < 32 stages L word t, 32 <= t < 72 stages R word t - 32, for all
-  // four byte-shifted copies (one pair of aligned global words -> 4 funnel shifts -> 4 STS)
-  const bool stager = tid < 72;
-  const bool st_left = tid < 32;
-  const int st_w = st_left ? tid : tid - 32;
+  // ---- staging roles: thread t < 32 stages L word t, 32 <= t < 32 + kRW stages R word t - 32, for all
+  // four byte-shifted copies (one pair of aligned global words -> 3 funnel shifts -> 4 STS)
+  const bool stager = tid < kLW + kRW;
+  const bool st_left = tid < kLW;
+  const int st_w = st_left ? tid : tid - kLW;
   const int st_kw = st_left ? kLW : kRW;
   const int st_off = (st_left ? 0 : 4 * kLW) + st_w;
   const uint32_t* st_g = st_left ? Lg : Rg;
@@ -122,81 +127,122 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
     }
   };
 
-  uint32_t V[4][8];
+  uint32_t V[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) V[i][j] = 0;
+    for (int j = 0; j < 4; ++j) V[i][j] = 0;
 
   __syncthreads();  // previous pass done with the ring; s_best init visible
   stage(0);
   __syncthreads();
 
-  const uint32_t* my_l = s_ring + p * kLW + 4 * ul;
-  const uint32_t* my_r = s_ring + 4 * kLW + dl * kRW + 4 * ul;
+  // this thread's operand words inside a ring row: L words [8ul, 8ul+8) of copy p; R words
+  // [rbase, rbase+12) of copy q, element (i, j) at rbase + (DIR<0 ? i - j + 4 : i + j)
+  const uint32_t* my_l = s_ring + p * kLW + 8 * ul;
+  const uint32_t* my_r = s_ring + 4 * kLW + q * kRW + 8 * ul + (DIR < 0 ? 4 - 4 * jh : 4 * jh);
+  // the window this lane owns after the reduce-scatter min: position 8*ul + own_i
+  const int own_i = ((dl >> 2) & 1) * 4 + ((dl >> 1) & 1) * 2 + (dl & 1);
+  const bool b4 = (dl >> 2) & 1, b3 = (dl >> 1) & 1, b2 = dl & 1;
+  uint32_t* my_best = s_best + p * 32 + 8 * ul + own_i;
+
   int slot_new = 0, slot_old = 0;
   const int n_blk = (rows_in + kRB - 1) / kRB;
   for (int blk = 0; blk < n_blk; ++blk) {
     stage((blk + 1) * kRB);  // ring depth >= th + 2*kRB keeps every row this block still needs intact
     const int r_end = min(rows_in, (blk + 1) * kRB);
     for (int row = blk * kRB; row < r_end; ++row) {
+      // all shared loads of this row up front (the old-row slot is harmless garbage while row < th)
+      const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot_new * kRowWords);
+      const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_new * kRowWords);
+      const uint4* lo = reinterpret_cast<const uint4*>(my_l + (size_t)slot_old * kRowWords);
+      const uint4* ro = reinterpret_cast<const uint4*>(my_r + (size_t)slot_old * kRowWords);
+      const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
+      const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
+      slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
       // ---- new row enters the window
       {
-        const uint4 l4 = *reinterpret_cast<const uint4*>(my_l + (size_t)slot_new * kRowWords);
-        const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_new * kRowWords);
-        const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-        const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
+        const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], V[i][j]);
-        slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
+          for (int j = 0; j < 4; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
       }
       // ---- old row leaves the window
       if (row >= th) {
-        const uint4 l4 = *reinterpret_cast<const uint4*>(my_l + (size_t)slot_old * kRowWords);
-        const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_old * kRowWords);
-        const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-        const uint32_t Lw[4] = {l4.x, l4.y, l4.z, l4.w};
-        const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+        const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 8 : i + j], 0u);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
             V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
           }
         slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
       }
       // ---- window sums, keys, running min
       if (row >= th - 1) {
-        uint32_t best[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        uint32_t best[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t pre1 = V[0][j], pre2 = pre1 + V[1][j], pre3 = pre2 + V[2][j], tot = pre3 + V[3][j];
-          uint32_t T0 = tot;
+        for (int i = 0; i < 8; ++i) best[i] = 0xffffffffu;
 #pragma unroll
-          for (int s = 1; s < Q; ++s) T0 += __shfl_down_sync(0xffffffffu, tot, s, 8);
-          const uint32_t h1 = __shfl_down_sync(0xffffffffu, pre1, Q, 8);
-          const uint32_t h2 = __shfl_down_sync(0xffffffffu, pre2, Q, 8);
-          const uint32_t h3 = __shfl_down_sync(0xffffffffu, pre3, Q, 8);
-          uint32_t T[4];
-          T[0] = T0; T[1] = T0 - pre1 + h1; T[2] = T0 - pre2 + h2; T[3] = T0 - pre3 + h3;
+        for (int jp = 0; jp < 4; jp += 2) {
+          uint32_t key[2][8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) best[i] = min(best[i], imad_u32(T[i], key_scale, code[MASKED ? i : 0][j]));
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = jp + jj;
+            // columns 8 .. 8+NW-2 come from the next u-lane (garbage for ul = 3: those positions are not emitted)
+            uint32_t Vx[8 + NW - 1];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Vx[i] = V[i][j];
+#pragma unroll
+            for (int c = 0; c < NW - 1; ++c) Vx[8 + c] = __shfl_down_sync(0xffffffffu, V[c][j], 1, 4);
+            uint32_t T = Vx[0];
+#pragma unroll
+            for (int k = 1; k < NW; ++k) T += Vx[k];
+            if (!MASKED) {
+              // slide the packed key itself: key_{i+1} = key_i + (Vx[i+NW] - Vx[i]) << xb, two IMADs on the
+              // FMA pipe (wrap-around arithmetic is exact: every true key fits in 32 bits)
+              uint32_t k = imad_u32(T, key_scale, code[0][j]);
+              key[jj][0] = k;
+#pragma unroll
+              for (int i = 0; i < 7; ++i) {
+                k = imad_u32(Vx[i], minus_scale, k);
+                k = imad_u32(Vx[i + NW], key_scale, k);
+                key[jj][i + 1] = k;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                key[jj][i] = imad_u32(T, key_scale, code[MASKED ? i : 0][j]);
+                if (i < 7) T = T - Vx[i] + Vx[i + NW];
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) best[i] = __vimin3_u32(best[i], key[0][i], key[1][i]);
+        }
+        // reduce-scatter min over the 8 d-lanes (lane bits 4, 3, 2): 4 + 2 + 1 shuffles, each lane ends
+        // with the minimum of one window
+        uint32_t h4[4], h2[2], h1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t keep = b4 ? best[4 + k] : best[k], send = b4 ? best[k] : best[4 + k];
+          h4[k] = min(keep, __shfl_xor_sync(0xffffffffu, send, 16));
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 8));
-          best[i] = min(best[i], __shfl_xor_sync(0xffffffffu, best[i], 16));
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t keep = b3 ? h4[2 + k] : h4[k], send = b3 ? h4[k] : h4[2 + k];
+          h2[k] = min(keep, __shfl_xor_sync(0xffffffffu, send, 8));
         }
-        if (dl == 0) {
-          uint4* bp = reinterpret_cast<uint4*>(s_best + ((size_t)(row - (th - 1)) * 4 + p) * 32 + 4 * ul);
-          uint4 b = *bp;
-          b.x = min(b.x, best[0]); b.y = min(b.y, best[1]); b.z = min(b.z, best[2]); b.w = min(b.w, best[3]);
-          *bp = b;
+        {
+          const uint32_t keep = b2 ? h2[1] : h2[0], send = b2 ? h2[0] : h2[1];
+          h1 = min(keep, __shfl_xor_sync(0xffffffffu, send, 4));
         }
+        uint32_t* bp = my_best + (size_t)(row - (th - 1)) * 128;
+        *bp = min(*bp, h1);
       }
     }
     __syncthreads();
@@ -206,20 +252,20 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
 // Q = tw / 16 (window = 4*Q packed words).
 template <int DIR, int Q>
-__global__ void __launch_bounds__(kDenseThreads, 3)
+__global__ void __launch_bounds__(kDenseThreads, 4)
 dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* s_ring = smem_u32;                                  // [nr][kRowWords]
   uint32_t* s_best = smem_u32 + (size_t)cfg.nr * kRowWords;     // [bh][4][32]
 
   const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;   // p: byte phase of this warp
-  const int ul = lane & 7, dl = lane >> 3;
+  const int ul = lane & 3, dl = lane >> 2;
   const int tile = blockIdx.x, band = blockIdx.y, pair = blockIdx.z;
   const int X0 = tile * cfg.stride_px;
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
   const int rows_in = bh + J.th - 1;
-  const int x0 = X0 + p + 16 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i)
+  const int x0 = X0 + p + 32 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i, i < 8)
   const uint32_t* Lg = reinterpret_cast<const uint32_t*>(J.left + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
   const uint32_t* Rg = reinterpret_cast<const uint32_t*>(J.right + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
   const int xb = cfg.xb;
@@ -232,22 +278,23 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   if (DIR < 0) { d_lo = max(J.dmin, X0 - (J.nxc - 1)); d_hi = min(J.dmax, x_hi); }
   else { d_lo = max(J.dmin, -x_hi); d_hi = min(J.dmax, J.nxc - 1 - X0); }
   d_lo = d_lo & ~3;  // floor to a multiple of 4 (also for negatives): keeps the R copies word aligned
-  // warp p, lane dl covers d = D0 + 4j + (p - dl) [LeftCam] / D0 + 4j + (dl - p) [RightCam], j < 8:
+  // warp p, d-lane (jh, q) covers d = D0 + 16jh + 4j + (p - q) [LeftCam] / ... + (q - p) [RightCam], j < 4:
   // every warp sees 32 consecutive d starting in [D0 - 3, D0]; the shortest reach is D0 + 28.
   const int n_pass = d_hi >= d_lo ? (d_hi - d_lo + 3) / 32 + 1 : 0;
 
   for (int pass = 0; pass < n_pass; ++pass) {
     const int D0 = d_lo + 32 * pass;
-    const int dbase = D0 + (DIR < 0 ? (p - dl) : (dl - p));  // d of (this lane, j = 0); d_j = dbase + 4j
+    // d of (this lane, j = 0); d_j = dbase + 4j, j < 4. dl = 4*jh + q: R copy q, upper/lower half of the 8 d-steps
+    const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
     // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
     // is every element of every lane of this warp a valid candidate? (windows beyond the frame do not count)
     bool all_ok = true;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const int d = dbase + 4 * j;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         const int x = x0 + 4 * i;
         const int xr = DIR < 0 ? x - d : x + d;
         all_ok = all_ok && ((d >= J.dmin && d <= J.dmax && xr >= 0 && xr <= J.nxc - 1) || x > J.nxc - 1);
@@ -276,7 +323,7 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     } else {
       const uint32_t raw = key >> xb;
       const int c = (int)(key & code_mask) - kCodeOff;  // = x0 -/+ d of the owning thread column 0
-      const int xr = c + 4 * (a & 3);
+      const int xr = c + 4 * (a & 7);
       write_result(J, g, (uint32_t)w, x, y, xr, raw, 0.0, normalised_cost(raw, USV_COST_SAD, J.n_elems));
     }
   }
@@ -298,12 +345,12 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   DenseCfg cfg;
   cfg.stride_px = 4 * (32 - 4 * q + 1);
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
-  cfg.xb = ceil_log2((long long)J.nxc + kCodeOff + 16 + 1);
+  cfg.xb = ceil_log2((long long)J.nxc + kCodeOff + 1);
   const long long smax = 255ll * J.n_elems;
   if (ceil_log2(smax + 1) + cfg.xb > 31) return cudaErrorNotSupported;  // bit 31 marks invalid candidates
   cfg.nr = J.th + 2 * kRB;
   // bands: as tall as shared memory allows (amortises the th-1 warm-up rows), but enough CTAs to fill 148 SMs
-  const int smem_budget = 72 * 1024;  // 3 CTAs / SM
+  const int smem_budget = 56 * 1024;  // 4 CTAs / SM
   int bh_max = (smem_budget - cfg.nr * kRowWords * 4) / 512;
   if (bh_max < 8) return cudaErrorNotSupported;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
