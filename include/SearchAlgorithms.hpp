@@ -1,0 +1,71 @@
+// SearchAlgorithms.hpp — the search entry points of the B200 path, named and shaped after
+// the reference's (P/SearchAlgorithms.hpp:28-43 declares the search family and
+// ColourSearchParameters; GenerateMatchingList / ResolveMatchList are defined at
+// P/Main.cpp:403-477 and declared in no header). The reference scores *contours* with
+// cv::matchShapes; this path scores *pixel blocks* (SAD / SSD / NCC / ZNCC) on the GPU, so the
+// contour overloads are replaced by image-view overloads with a BlockSearchSpec. Loop order
+// (template-major, candidate-minor, P/Main.cpp:408-410), the accept test (`< 0.75`, :417) and
+// the strict-'>' replacement rule (:451) are the reference's.
+//
+// Out of scope here (contour pre-processing): MorphilogicalFilter,
+// ABSDiffSearch, ColourSearch, CannySearch.
+#ifndef SearchAlgorithms_HPP
+#define SearchAlgorithms_HPP
+
+#include <vector>
+
+#include "DistanceCalculator.hpp"
+#include "Match.hpp"
+#include "usv_cv_compat.hpp"
+
+// Kept verbatim in meaning from the reference (P/SearchAlgorithms.hpp:28-33): HSV thresholds of
+// the colour segmentation that used to generate candidates. Unused by the block search.
+struct ColourSearchParameters {
+  int iLowHue, iLowSaturation, iLowValue, iHighHue, iHighSaturation, iHighValue, iLowHue2, iHighHue2;
+};
+
+// What to score and where to look (the reference hard-codes its equivalents: accept 0.75 at
+// P/Main.cpp:417, 640x480 at P/DistanceCalculator.hpp:22-23).
+struct BlockSearchSpec {
+  enum CostKind { SAD = 0, SSD = 1, NCC = 2, ZNCC = 3 };
+  enum DistanceKind { NoDistance = 0, Pinhole = 1, PowerLaw = 2 };
+  int TemplateWidth = 16, TemplateHeight = 16;
+  int SearchMin = 0, SearchMax = 1 << 20;  // disparity range, clipped to the frame
+  int StrideX = 1, StrideY = 1;            // window grid of the dense overload
+  CostKind Cost = SAD;
+  DistanceKind Distance = Pinhole;
+  double AcceptThreshold = 0.75;  // accept iff MatchValue < this (P/Main.cpp:417)
+  bool CameraSide = LeftCam;      // which camera ThisCamera is
+  int Device = 0;                 // CUDA device of the calling thread's context
+};
+
+// Dense sweep: every window of the grid over ThisCamera against its candidates on the same row
+// of OtherCamera. Appends, in window order, the best ACCEPTED match of each window — what
+// GenerateMatchingList followed by ResolveMatchList yields for one template's candidates
+// (TentativeMatch[0], the first minimum). LeftIndex = window index (row-major), RightIndex =
+// y * (width - TemplateWidth + 1) + x'. `Distances` (optional) receives the distance of each
+// appended match. The caller clears the outputs, as in the reference (P/Main.cpp:842-871).
+void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView& OtherCamera, const BlockSearchSpec& Spec,
+                          std::vector<Match>& Matcher, std::vector<double>* Distances = nullptr);
+
+// Explicit templates: the reference's semantics in full — EVERY candidate whose cost passes the
+// accept test is appended as {i, j, cost}, i = template index (outer loop), j = candidate
+// position x' (inner loop, ascending). Feed the result to ResolveMatchList.
+void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView& OtherCamera,
+                          std::vector<cv::Point> Templates, const BlockSearchSpec& Spec, std::vector<Match>& Matcher);
+
+// P/Main.cpp:432-477, behaviour for behaviour (one greedy pass; a later match replaces every
+// earlier tentative entry sharing Left or Right index that is strictly worse; appended when it
+// replaced nothing). Used for cross-template uniqueness over the per-window winners.
+void ResolveMatchList(std::vector<Match> Matcher, std::vector<Match>& TentativeMatch);
+
+// One call per frame pair in the reference's call order (P/Main.cpp:1115-1143, then the inline
+// disparity/distance of :681-694): generate -> resolve -> distance. Returns 0, or -1 on an
+// empty frame / GPU error like the reference's thread entry points (:908-911).
+int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,
+                const BlockSearchSpec& Spec, std::vector<Match>& ExportMatches, std::vector<double>& ExportDistances);
+
+// Last error text of the calling thread's GPU context ("" when none).
+const char* BlockSearchLastError();
+
+#endif /* SearchAlgorithms_HPP */

@@ -1,0 +1,135 @@
+// SearchAlgorithms.cpp — host side of the block-search drop-in. Every cost is computed by the
+// sm_100a kernels behind the C-ABI; this file only marshals vectors, applies the accept test to
+// dumped candidate costs (template overload) and restates ResolveMatchList.
+#include "../../../include/SearchAlgorithms.hpp"
+
+#include <cmath>
+#include <cstring>
+
+#include "usv_host_ctx.hpp"
+
+static usv_search_params to_params(const BlockSearchSpec& s) {
+  usv_search_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.tmpl_w = s.TemplateWidth; p.tmpl_h = s.TemplateHeight;
+  p.search_min = s.SearchMin; p.search_max = s.SearchMax;
+  p.stride_x = s.StrideX; p.stride_y = s.StrideY;
+  p.cost_kind = (int)s.Cost;
+  p.camera_side = s.CameraSide == LeftCam ? USV_LEFT_CAM : USV_RIGHT_CAM;
+  p.distance_kind = (int)s.Distance;
+  p.accept_threshold = s.AcceptThreshold;
+  return p;
+}
+
+static bool same_geometry(const usv::ImageView& a, const usv::ImageView& b) {
+  return a.data && b.data && a.width == b.width && a.height == b.height && a.channels == b.channels && a.step == b.step;
+}
+
+static usv_frame_desc to_frame(const usv::ImageView& v) {
+  usv_frame_desc f;
+  f.width = v.width; f.height = v.height; f.channels = v.channels;
+  f.row_stride = (int32_t)v.step;
+  f.frame_stride = (int64_t)v.step * v.height;
+  return f;
+}
+
+const char* BlockSearchLastError() { return usv::thread_contexts().last_error.c_str(); }
+
+void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView& OtherCamera, const BlockSearchSpec& Spec,
+                          std::vector<Match>& Matcher, std::vector<double>* Distances) {
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  if (!same_geometry(ThisCamera, OtherCamera)) { tc.last_error = "GenerateMatchingList: frames empty or of different geometry"; return; }
+  usv_ctx* ctx = tc.get(Spec.Device);
+  if (!ctx) return;
+  const usv_search_params p = to_params(Spec);
+  const usv_frame_desc f = to_frame(ThisCamera);
+  int32_t nx = 0, ny = 0;
+  if (usv_grid_dims(&f, &p, &nx, &ny, nullptr) != USV_OK) { tc.last_error = "GenerateMatchingList: template does not fit the frame"; return; }
+  const size_t n = (size_t)nx * ny;
+  std::vector<usv_match> rec(n);
+  std::vector<double> dist(Distances ? n : 0);
+  usv_outputs out;
+  std::memset(&out, 0, sizeof(out));
+  out.matches = rec.data();
+  if (Distances) out.distance = dist.data();
+  const int rc = usv_match_dense_host(ctx, ThisCamera.data, OtherCamera.data, &f, 1, &p, &out);
+  if (!tc.check(ctx, rc, "usv_match_dense_host")) return;
+  for (size_t i = 0; i < n; ++i) {
+    if (rec[i].RightIndex == USV_NO_MATCH) continue;  // no candidate passed `< AcceptThreshold` (P/Main.cpp:417)
+    Matcher.push_back({rec[i].LeftIndex, rec[i].RightIndex, rec[i].MatchValue});
+    if (Distances) Distances->push_back(dist[i]);
+  }
+}
+
+void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView& OtherCamera, std::vector<cv::Point> Templates,
+                          const BlockSearchSpec& Spec, std::vector<Match>& Matcher) {
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  if (!same_geometry(ThisCamera, OtherCamera)) { tc.last_error = "GenerateMatchingList: frames empty or of different geometry"; return; }
+  if (Templates.empty()) return;  // P/Main.cpp:405
+  usv_ctx* ctx = tc.get(Spec.Device);
+  if (!ctx) return;
+  const usv_search_params p = to_params(Spec);
+  const usv_frame_desc f = to_frame(ThisCamera);
+  const int nt = (int)Templates.size(), cap = f.width;
+  std::vector<int32_t> tx(nt), ty(nt);
+  for (int i = 0; i < nt; ++i) { tx[i] = Templates[i].x; ty[i] = Templates[i].y; }
+  const bool integer = p.cost_kind <= USV_COST_SSD;
+  std::vector<uint32_t> cost_rows(integer ? (size_t)nt * cap : 0);
+  std::vector<double> score_rows(integer ? 0 : (size_t)nt * cap);
+  usv_outputs out;
+  std::memset(&out, 0, sizeof(out));
+  const int rc = usv_match_templates_host(ctx, ThisCamera.data, OtherCamera.data, &f, 1, tx.data(), ty.data(), nt, &p, &out,
+                                          integer ? cost_rows.data() : nullptr, integer ? nullptr : score_rows.data(), cap);
+  if (!tc.check(ctx, rc, "usv_match_templates_host")) return;
+  const int nxc = f.width - p.tmpl_w + 1;
+  const double n_elems = (double)p.tmpl_w * p.tmpl_h * f.channels;
+  const double den = p.cost_kind == USV_COST_SAD ? 255.0 * n_elems : 65025.0 * n_elems;
+  for (int i = 0; i < nt; ++i) {  // template-major (P/Main.cpp:408)
+    int lo, hi;
+    if (p.camera_side == USV_LEFT_CAM) { lo = tx[i] - p.search_max; hi = tx[i] - p.search_min; }
+    else { lo = tx[i] + p.search_min; hi = tx[i] + p.search_max; }
+    if (lo < 0) lo = 0;
+    if (hi > nxc - 1) hi = nxc - 1;
+    for (int xr = lo; xr <= hi; ++xr) {  // candidate-minor, ascending x' (P/Main.cpp:410)
+      const size_t k = (size_t)i * cap + (xr - lo);
+      const double v = integer ? (double)cost_rows[k] / den : 1.0 - score_rows[k];
+      if (v < Spec.AcceptThreshold)  // Is it at least a partial match? (P/Main.cpp:417)
+        Matcher.push_back({(unsigned)i, (unsigned)(ty[i] * nxc + xr), v});
+    }
+  }
+}
+
+// P/Main.cpp:432-477. The outer while(AnyConflict) of the reference runs its body once (Matcher is
+// cleared at :475 and MatchCounter is never reset), DeassignedMatch is write-only: what remains is
+// this single greedy pass.
+void ResolveMatchList(std::vector<Match> Matcher, std::vector<Match>& TentativeMatch) {
+  TentativeMatch.clear();
+  for (size_t k = 0; k < Matcher.size(); ++k) {
+    bool Conflict = false;
+    for (size_t i = 0; i < TentativeMatch.size(); ++i) {
+      if (TentativeMatch[i].LeftIndex == Matcher[k].LeftIndex || TentativeMatch[i].RightIndex == Matcher[k].RightIndex) {  // :450
+        if (TentativeMatch[i].MatchValue > Matcher[k].MatchValue) {  // :451 — strictly worse only
+          TentativeMatch[i] = Matcher[k];
+          Conflict = true;
+        }
+      }
+    }
+    if (!Conflict) TentativeMatch.push_back(Matcher[k]);  // :463-466, :469
+  }
+}
+
+int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,
+                const BlockSearchSpec& Spec, std::vector<Match>& ExportMatches, std::vector<double>& ExportDistances) {
+  if (!ImportGrayThisCamera || !ImportGrayOtherCamera || !ImportGrayThisCamera->data || !ImportGrayOtherCamera->data ||
+      ImportGrayThisCamera->width <= 0 || ImportGrayThisCamera->height <= 0) {
+    usv::thread_contexts().last_error = "BlockSearch: empty frame";
+    return -1;  // P/Main.cpp:908-911
+  }
+  BlockSearchSpec s = Spec;
+  s.CameraSide = CameraSide;
+  ExportMatches.clear();
+  ExportDistances.clear();
+  // generate + per-window resolve are one fused kernel; the distance is its epilogue
+  GenerateMatchingList(*ImportGrayThisCamera, *ImportGrayOtherCamera, s, ExportMatches, &ExportDistances);
+  return usv::thread_contexts().last_error.empty() ? 0 : -1;
+}
