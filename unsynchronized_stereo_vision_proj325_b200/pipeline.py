@@ -1,0 +1,89 @@
+"""Unsynchronised-streams driver: host nearest-timestamp pairing, sharding of the paired frames
+over ranks (one process per GPU, no data-path collective) and streamed matching through the
+pinned ring. Replaces the reference's two free-running CameraThread loops (P/Main.cpp:738-1309:
+capture + timestamp :876-879, exchange of the other camera's data :1100-1113) for offline /
+synthetic streams (BASELINE.json configs[4], "C5")."""
+import numpy as np
+
+from . import _abi, api
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block of `n_items` owned by `rank`: item p goes to rank floor(p * world / n_items)
+    (SURVEY.md 8e). Returns (start, stop)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    start = -(-rank * n_items // world)
+    stop = -(-(rank + 1) * n_items // world)
+    return start, stop
+
+
+def pair_streams(t_left, t_right, max_dt):
+    """Nearest-timestamp pairing on the host (C-ABI usv_pair_nearest). Returns (left_idx, right_idx, dt)."""
+    li, ri = api.pair_nearest(t_left, t_right, max_dt)
+    dt = np.asarray(t_left)[li] - np.asarray(t_right)[ri]
+    return li, ri, dt
+
+
+def default_matcher(ctx, frame, params, pairs_per_slot, n_slots, mask):
+    """The product matcher: a usv_stream over `ctx` (GPU only)."""
+    return ctx.stream(frame, params, pairs_per_slot=pairs_per_slot, n_slots=n_slots, mask=mask)
+
+
+def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0 / 60.0, rank=0, world=1, ctx=None,
+                  pairs_per_slot=16, n_slots=3, mask=_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST, stream_factory=default_matcher):
+    """Pair two unsynchronised streams and match this rank's shard of the pairs.
+
+    frames_*: [n, H, W(, C)] uint8 arrays (host) indexed by frame number; t_*: ascending timestamps.
+    Returns dict(pair_left, pair_right, dt — for this rank's pairs — and one array per output in `mask`).
+    `stream_factory(ctx, frame, params, pairs_per_slot, n_slots, mask)` must return an object with the
+    usv_stream interface (slots / submit / wait / close); tests inject a CPU stub to exercise the host logic.
+    """
+    li, ri, dt = pair_streams(t_left, t_right, max_dt)
+    lo, hi = shard_range(len(li), rank, world)
+    li, ri, dt = li[lo:hi], ri[lo:hi], dt[lo:hi]
+    n = len(li)
+    h, w = frames_left.shape[1:3]
+    c = frames_left.shape[3] if frames_left.ndim == 4 else 1
+    frame = _abi.FrameDesc(w, h, c, w * c, w * c * h)
+    st = stream_factory(ctx, frame, params, pairs_per_slot, n_slots, mask)
+    outs = {name: [] for name, bit, _ in _abi.OUTPUT_FIELDS if mask & bit}
+    pending = []  # (slot, count) in submission order
+
+    def drain_one():
+        slot, cnt = pending.pop(0)
+        st.wait(slot)
+        for k in outs:
+            outs[k].append(st.slots[slot]["out"][k][:cnt].copy())
+
+    for b0 in range(0, n, pairs_per_slot):
+        slot = (b0 // pairs_per_slot) % n_slots
+        if len(pending) == n_slots:
+            drain_one()  # the oldest in-flight batch owns this slot
+        cnt = min(pairs_per_slot, n - b0)
+        # "capture": the paired frames land in the slot's pinned buffers
+        st.slots[slot]["left"][:cnt] = frames_left[li[b0:b0 + cnt]].reshape(cnt, h, w * c)
+        st.slots[slot]["right"][:cnt] = frames_right[ri[b0:b0 + cnt]].reshape(cnt, h, w * c)
+        st.submit(slot, cnt)
+        pending.append((slot, cnt))
+    while pending:
+        drain_one()
+    st.close()
+    res = {"pair_left": li, "pair_right": ri, "dt": dt}
+    for k, v in outs.items():
+        res[k] = np.concatenate(v, axis=0) if v else np.zeros((0, 0), dtype=dict((n_, d) for n_, _, d in _abi.OUTPUT_FIELDS)[k])
+    return res
+
+
+def gather_on_host(local, rank, world, group=None):
+    """Host-side gather of per-rank result dicts onto rank 0 in rank (= pair) order. Uses
+    torch.distributed only as plumbing (gloo or nccl-backed object gather); returns the merged dict on
+    rank 0 and None elsewhere."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object(local, bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    return {k: np.concatenate([b[k] for b in bucket], axis=0) for k in local}
