@@ -59,6 +59,12 @@ void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView
 // replaced nothing). Used for cross-template uniqueness over the per-window winners.
 void ResolveMatchList(std::vector<Match> Matcher, std::vector<Match>& TentativeMatch);
 
+// P/Main.cpp:483-499: joins the current and the previous inter-frame match lists on
+// cur.RightIndex == old.LeftIndex. Output exactly as the reference produces it: because of the comma
+// operator in `(Point3i)(cur, old.RightIndex)` (:492) every triple is (old.RightIndex, 0, 0).
+void IDMatcher(std::vector<Match> InterframeMatchIndexes, std::vector<Match> OldInterframeMatchIndexes,
+               std::vector<cv::Point3i>& InterframeMatchIndexesComplete);
+
 // One call per frame pair in the reference's call order (P/Main.cpp:1115-1143, then the inline
 // disparity/distance of :681-694): generate -> resolve -> distance. Returns 0, or -1 on an
 // empty frame / GPU error like the reference's thread entry points (:908-911).

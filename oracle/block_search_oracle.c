@@ -316,6 +316,25 @@ int64_t usv_oracle_resolve_match_list(const usv_match *in, int64_t n,
 }
 
 /*
+ * IDMatcher restated (P/Main.cpp:483-499): joins the current and the previous inter-frame match
+ * lists on cur.RightIndex == old.LeftIndex. The reference pushes
+ * `(Point3i)(cur[i], old[j].RightIndex)` (:492) — a comma operator, so the triple it stores is
+ * (old[j].RightIndex, 0, 0), not (cur.Left, cur.Right, old.Right). Kept as is.
+ */
+int64_t usv_oracle_id_matcher(const usv_match *cur, int64_t n_cur, const usv_match *old, int64_t n_old, int32_t *out3,
+                              int64_t cap) {
+  int64_t n = 0;
+  for (int64_t i = 0; i < n_cur; ++i)
+    for (int64_t j = 0; j < n_old; ++j)
+      if (cur[i].RightIndex == old[j].LeftIndex) {
+        if (n >= cap) return -1;
+        out3[3 * n] = (int32_t)old[j].RightIndex; out3[3 * n + 1] = 0; out3[3 * n + 2] = 0;
+        ++n;
+      }
+  return n;
+}
+
+/*
  * Nearest-timestamp pairing oracle (the synthetic replacement for the capture
  * loop's timestamps, P/Main.cpp:876-905). O(nL*nR) brute force on purpose:
  * every left frame picks the right frame with the smallest |tL-tR| (lowest

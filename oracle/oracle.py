@@ -53,6 +53,7 @@ def lib():
         L.usv_oracle_rad2deg.argtypes = [C.c_double]
         L.usv_oracle_resolve_match_list.restype = C.c_int64
         L.usv_oracle_pair_nearest.restype = C.c_int64
+        L.usv_oracle_id_matcher.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -68,6 +69,7 @@ def ref():
                 return None
         R = C.CDLL(REF_SO)
         R.ref_resolve_match_list.restype = C.c_int64
+        R.ref_id_matcher.restype = C.c_int64
         R.ref_deg2rad.restype = C.c_double
         R.ref_deg2rad.argtypes = [C.c_double]
         R.ref_rad2deg.restype = C.c_double
@@ -166,6 +168,25 @@ def resolve_match_list(matches):
 
 def ref_resolve_match_list(matches):
     return _resolve(ref().ref_resolve_match_list, matches)
+
+
+def _id_matcher(fn, cur, old):
+    a = np.ascontiguousarray(cur, dtype=_abi.MATCH_DTYPE)
+    b = np.ascontiguousarray(old, dtype=_abi.MATCH_DTYPE)
+    cap = max(len(a) * len(b), 1)
+    out = np.zeros((cap, 3), np.int32)
+    n = fn(_ptr(a), C.c_int64(len(a)), _ptr(b), C.c_int64(len(b)), _ptr(out), C.c_int64(cap))
+    if n < 0:
+        raise RuntimeError("id matcher failed")
+    return out[:n]
+
+
+def id_matcher(cur, old):
+    return _id_matcher(lib().usv_oracle_id_matcher, cur, old)
+
+
+def ref_id_matcher(cur, old):
+    return _id_matcher(ref().ref_id_matcher, cur, old)
 
 
 def _f32(a):

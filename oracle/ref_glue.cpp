@@ -16,6 +16,8 @@ using namespace std;
 
 // P/Main.cpp:432-477, extracted by the Makefile
 #include "resolve_extract.inc"
+// P/Main.cpp:483-499, extracted by the Makefile
+#include "idmatcher_extract.inc"
 
 extern "C" {
 
@@ -30,6 +32,17 @@ int64_t ref_resolve_match_list(const ref_match_pod* in, int64_t n, ref_match_pod
   if ((int64_t)t.size() > cap) return -1;
   for (size_t i = 0; i < t.size(); ++i) out[i] = {t[i].LeftIndex, t[i].RightIndex, t[i].MatchValue};
   return (int64_t)t.size();
+}
+
+int64_t ref_id_matcher(const ref_match_pod* cur, int64_t n_cur, const ref_match_pod* old, int64_t n_old, int32_t* out3, int64_t cap) {
+  std::vector<Match> a, b;
+  for (int64_t i = 0; i < n_cur; ++i) a.emplace_back(cur[i].LeftIndex, cur[i].RightIndex, cur[i].MatchValue);
+  for (int64_t i = 0; i < n_old; ++i) b.emplace_back(old[i].LeftIndex, old[i].RightIndex, old[i].MatchValue);
+  std::vector<Point3i> c;
+  IDMatcher(a, b, c);
+  if ((int64_t)c.size() > cap) return -1;
+  for (size_t i = 0; i < c.size(); ++i) { out3[3 * i] = c[i].x; out3[3 * i + 1] = c[i].y; out3[3 * i + 2] = c[i].z; }
+  return (int64_t)c.size();
 }
 
 static std::vector<Point2f> pts(const float* xy, int n) {

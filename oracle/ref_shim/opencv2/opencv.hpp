@@ -21,10 +21,19 @@ template <typename T> inline Point_<T> operator-(const Point_<T>& a, const Point
 // plain float multiply / divide.
 template <typename T> inline Point_<T> operator*(const Point_<T>& a, float b) { return Point_<T>(T(a.x * b), T(a.y * b)); }
 template <typename T> inline Point_<T> operator/(const Point_<T>& a, float b) { return Point_<T>(T(a.x / b), T(a.y / b)); }
+// OpenCV 3.0 Vec: a single-value constructor zero-fills the rest (core/matx.hpp); Point3_ converts from
+// Vec<T,3> (core/types.hpp). Needed for the reference's `(Point3i)(a, b)` comma-operator cast at
+// P/Main.cpp:492, which ends up constructing Point3i(Vec3i(b)) = (b, 0, 0).
+template <typename T, int n> struct Vec {
+  T val[n];
+  Vec() { for (int i = 0; i < n; ++i) val[i] = T(0); }
+  Vec(T v0) { val[0] = v0; for (int i = 1; i < n; ++i) val[i] = T(0); }
+};
 template <typename T> struct Point3_ {
   T x, y, z;
   Point3_() : x(0), y(0), z(0) {}
   Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
+  Point3_(const Vec<T, 3>& v) : x(v.val[0]), y(v.val[1]), z(v.val[2]) {}
 };
 typedef Point_<int> Point2i;
 typedef Point2i Point;

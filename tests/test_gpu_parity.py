@@ -75,6 +75,10 @@ SWEEP = [
     (96, 33, 3, 6, dict(tmpl_w=11, tmpl_h=4, cost="sad", stride_x=2, stride_y=3, search_max=40)),
     (64, 64, 1, 5, dict(tmpl_w=64, tmpl_h=64, cost="ssd")),                                      # one window, max template
     (600, 24, 1, 3, dict(tmpl_w=16, tmpl_h=16, cost="sad", search_min=-8, search_max=8)),         # signed range
+    (400, 30, 1, 21, dict(tmpl_w=8, tmpl_h=8, cost="sad", search_max=90)),                        # dense kernel, 2-word windows
+    (400, 30, 1, 21, dict(tmpl_w=12, tmpl_h=9, cost="sad", search_max=90)),                       # 3-word windows
+    (400, 40, 1, 21, dict(tmpl_w=24, tmpl_h=24, cost="sad")),                                     # 6-word windows, full range
+    (400, 40, 1, -21, dict(tmpl_w=32, tmpl_h=20, cost="sad", camera_side=_abi.RIGHT_CAM)),         # 8-word windows, RightCam
 ]
 
 

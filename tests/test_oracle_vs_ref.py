@@ -152,3 +152,18 @@ def test_deg_rad(oracle, ref):
     for v in (0.0, 1.0, 45.0, 70.0, 180.0, -33.3):
         assert oracle.lib().usv_oracle_deg2rad(v) == ref.ref_deg2rad(v)
         assert oracle.lib().usv_oracle_rad2deg(v) == ref.ref_rad2deg(v)
+
+
+def test_id_matcher_vs_ref(oracle, ref):
+    """IDMatcher (P/Main.cpp:483-499) incl. the comma-operator quirk at :492: triples are (old.Right, 0, 0)."""
+    cur = _m([(0, 5, .1), (1, 7, .2), (2, 5, .3)])
+    old = _m([(5, 9, .1), (7, 3, .2), (8, 1, .3)])
+    assert oracle.ref_id_matcher(cur, old).tolist() == [[9, 0, 0], [3, 0, 0], [9, 0, 0]]
+    rng = np.random.default_rng(4)
+    for _ in range(100):
+        a = np.zeros(int(rng.integers(0, 12)), dtype=M)
+        b = np.zeros(int(rng.integers(0, 12)), dtype=M)
+        for z in (a, b):
+            z["LeftIndex"] = rng.integers(0, 6, len(z))
+            z["RightIndex"] = rng.integers(0, 6, len(z))
+        assert oracle.id_matcher(a, b).tolist() == oracle.ref_id_matcher(a, b).tolist()

@@ -118,6 +118,17 @@ void ResolveMatchList(std::vector<Match> Matcher, std::vector<Match>& TentativeM
   }
 }
 
+// P/Main.cpp:483-499 (a tiny O(n*m) host join; its output feeds MovingObjectDistanceCalculator's index triples)
+void IDMatcher(std::vector<Match> InterframeMatchIndexes, std::vector<Match> OldInterframeMatchIndexes,
+               std::vector<cv::Point3i>& InterframeMatchIndexesComplete) {
+  InterframeMatchIndexesComplete.clear();  // :486
+  for (size_t i = 0; i < InterframeMatchIndexes.size(); ++i)
+    for (size_t j = 0; j < OldInterframeMatchIndexes.size(); ++j)
+      if (InterframeMatchIndexes[i].RightIndex == OldInterframeMatchIndexes[j].LeftIndex)  // :491
+        // :492 `(Point3i)(cur, old.RightIndex)`: the comma operator keeps only old.RightIndex -> (old.RightIndex, 0, 0)
+        InterframeMatchIndexesComplete.push_back(cv::Point3i((int)OldInterframeMatchIndexes[j].RightIndex, 0, 0));
+}
+
 int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,
                 const BlockSearchSpec& Spec, std::vector<Match>& ExportMatches, std::vector<double>& ExportDistances) {
   if (!ImportGrayThisCamera || !ImportGrayOtherCamera || !ImportGrayThisCamera->data || !ImportGrayOtherCamera->data ||

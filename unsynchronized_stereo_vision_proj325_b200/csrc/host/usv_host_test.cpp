@@ -39,6 +39,14 @@ int main(int argc, char** argv) {
     CHECK(out.size() == 2 && out[0].LeftIndex == 0 && out[0].RightIndex == 1 && out[1].RightIndex == 1);
   }
 
+  // ---- IDMatcher: the reference's join, comma-operator quirk included (P/Main.cpp:492)
+  {
+    std::vector<Match> cur = {{0, 5, .1}, {1, 7, .2}, {2, 5, .3}}, old = {{5, 9, .1}, {7, 3, .2}, {8, 1, .3}};
+    std::vector<cv::Point3i> c;
+    IDMatcher(cur, old, c);
+    CHECK(c.size() == 3 && c[0].x == 9 && c[0].y == 0 && c[0].z == 0 && c[1].x == 3 && c[2].x == 9);
+  }
+
   // ---- synthetic rectified pair: right[y][x] = left[y][x + 37]
   const int W = 640, H = 64, SHIFT = 37;
   std::vector<uint8_t> L((size_t)W * H), R((size_t)W * H);

@@ -63,7 +63,7 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // MASKED = false: every (i, j) element of every lane is a valid candidate -> 4 code registers.
 // MASKED = true : per-element codes; an invalid candidate carries bit 31 in its code and can
 //                 never beat a valid one (valid keys stay below 2^31, checked on the host).
-template <int DIR, int Q, bool MASKED>
+template <int DIR, int NW, bool MASKED>
 __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
                                            const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
                                            const int XR0, const int x0, const int dbase, const int rows_in,
@@ -74,7 +74,6 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const int row_words = J.row_stride >> 2;
   const uint32_t key_scale = 1u << cfg.xb;
   const uint32_t minus_scale = key_scale * minus_one;  // -(1 << xb), kept opaque so the multiply stays an IMAD
-  constexpr int NW = 4 * Q;  // packed words per window
 
   constexpr int NC = MASKED ? 8 : 1;
   uint32_t code[NC][4];
@@ -255,8 +254,8 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 }
 
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
-// Q = tw / 16 (window = 4*Q packed words).
-template <int DIR, int Q>
+// NW = tw / 4 packed words per window (2..8: the halo columns come from one neighbouring lane).
+template <int DIR, int NW>
 __global__ void __launch_bounds__(kDenseThreads, 4)
 dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -306,13 +305,13 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
       }
     }
     // the choice must be CTA-uniform in control flow (both variants contain the same barriers), warp-uniform in data
-    if (__all_sync(0xffffffffu, all_ok)) dense_pass<DIR, Q, false>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
-    else dense_pass<DIR, Q, true>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
+    if (__all_sync(0xffffffffu, all_ok)) dense_pass<DIR, NW, false>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
+    else dense_pass<DIR, NW, true>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
   }
   __syncthreads();
 
   // ---- fused epilogue: key -> (cost, x') -> Match / disparity / distance
-  const int n_pos = 32 - 4 * Q + 1;  // valid window positions per phase in a tile
+  const int n_pos = 32 - NW + 1;  // valid window positions per phase in a tile
   const int span = min(cfg.stride_px, J.nxc - X0);
   const uint32_t code_mask = (1u << xb) - 1;
   for (int idx = tid; idx < bh * span; idx += kDenseThreads) {
@@ -344,11 +343,11 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   // coverage of the sliding-window kernels; everything else runs on the direct-form kernel
   if (J.tx || J.channels != 1 || J.sx != 1 || J.sy != 1) return cudaErrorNotSupported;
   if (J.cost_kind != USV_COST_SAD) return cudaErrorNotSupported;
-  if (J.tw % 16 != 0 || J.tw > 32 || J.th > 64) return cudaErrorNotSupported;
+  const int nw = J.tw / 4;
+  if (J.tw % 4 != 0 || !(nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) || J.th > 64) return cudaErrorNotSupported;
   if (J.out.score) { /* score is 0 for integer kinds; write_result handles it */ }
-  const int q = J.tw / 16;
   DenseCfg cfg;
-  cfg.stride_px = 4 * (32 - 4 * q + 1);
+  cfg.stride_px = 4 * (32 - nw + 1);
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
   cfg.xb = ceil_log2((long long)J.nxc + kCodeOff + 1);
   const long long smax = 255ll * J.n_elems;
@@ -364,15 +363,23 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = (size_t)cfg.nr * kRowWords * 4 + (size_t)cfg.bh * 512;
   dim3 grid(cfg.n_xtiles, cfg.n_bands, n_pairs), block(kDenseThreads);
-#define USV_DENSE_LAUNCH(D, QQ)                                                                           \
+#define USV_DENSE_LAUNCH(D, NWW)                                                                          \
   {                                                                                                       \
-    auto kfn = dense_sad_argmin_kernel<D, QQ>;                                                            \
+    auto kfn = dense_sad_argmin_kernel<D, NWW>;                                                           \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     if (e != cudaSuccess) return e;                                                                       \
     kfn<<<grid, block, smem, st>>>(J, cfg, 0xffffffffu);                                                  \
   }
-  if (J.camera_side == USV_LEFT_CAM) { if (q == 1) USV_DENSE_LAUNCH(-1, 1) else USV_DENSE_LAUNCH(-1, 2) }
-  else { if (q == 1) USV_DENSE_LAUNCH(1, 1) else USV_DENSE_LAUNCH(1, 2) }
+#define USV_DENSE_BY_NW(D)                                                                                \
+  switch (nw) {                                                                                           \
+    case 2: USV_DENSE_LAUNCH(D, 2) break;                                                                 \
+    case 3: USV_DENSE_LAUNCH(D, 3) break;                                                                 \
+    case 4: USV_DENSE_LAUNCH(D, 4) break;                                                                 \
+    case 6: USV_DENSE_LAUNCH(D, 6) break;                                                                 \
+    default: USV_DENSE_LAUNCH(D, 8) break;                                                                \
+  }
+  if (J.camera_side == USV_LEFT_CAM) { USV_DENSE_BY_NW(-1) } else { USV_DENSE_BY_NW(1) }
+#undef USV_DENSE_BY_NW
 #undef USV_DENSE_LAUNCH
   *kernel_name = "dense_sad_argmin_kernel";
   *n_launches = 1;
