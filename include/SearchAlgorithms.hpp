@@ -39,6 +39,12 @@ struct BlockSearchSpec {
   int Device = 0;                 // CUDA device of the calling thread's context
 };
 
+// The reference's own signature, unchanged (P/Main.cpp:403): contours of this camera vs contours of the
+// other, cost = matchShapes(I1) + relative area difference (:413-415) evaluated on the GPU for all pairs,
+// every pair with cost < 0.75 appended as {i, j, cost} in i-major / j-minor order (:408-422).
+void GenerateMatchingList(std::vector<std::vector<cv::Point> > UsefulContoursL, std::vector<std::vector<cv::Point> > UsefulContoursR,
+                          std::vector<Match>& Matcher);
+
 // Dense sweep: every window of the grid over ThisCamera against its candidates on the same row
 // of OtherCamera. Appends, in window order, the best ACCEPTED match of each window — what
 // GenerateMatchingList followed by ResolveMatchList yields for one template's candidates

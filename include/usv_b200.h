@@ -164,6 +164,20 @@ int usv_match_templates_host(usv_ctx *ctx, const uint8_t *h_left,
                              const usv_outputs *h_out, uint32_t *h_cost_rows,
                              double *h_score_rows, int32_t row_cap);
 
+/* ---- the reference's ORIGINAL cost: contour shape + size (P/Main.cpp:403-426) ----
+ * cost(i, j) = cv::matchShapes(This[i], Other[j], CONTOURS_MATCH_I1, 0)
+ *              + |area_i - area_j| / ((area_i + area_j) / 2)            (:413-415)
+ * evaluated on the GPU for every pair; matches with cost < accept_threshold (:417) are written in
+ * i-major / j-minor order (:408-410). Contours are concatenated (x, y) int32 pairs with CSR offsets
+ * (off[k] .. off[k+1] are the points of contour k). cost_matrix (optional): all n_this * n_other
+ * costs. Host pointers. */
+int usv_match_contours(usv_ctx *ctx, const int32_t *pts_this,
+                       const int32_t *off_this, int32_t n_this,
+                       const int32_t *pts_other, const int32_t *off_other,
+                       int32_t n_other, double accept_threshold,
+                       usv_match *h_out, int64_t cap, int64_t *n_out,
+                       double *h_cost_matrix);
+
 /* ---- distance family (host buffers; one tiny kernel each) ---------------- */
 int usv_disparity_to_distance(usv_ctx *ctx, const int32_t *h_disp, int64_t n,
                               int32_t distance_kind, double *h_dist);

@@ -40,7 +40,7 @@ def _stale(target, deps):
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(HERE, f) for f in ("block_search_oracle.c", "distance_oracle.c", "Makefile")]
+        srcs = [os.path.join(HERE, f) for f in ("block_search_oracle.c", "distance_oracle.c", "contour_oracle.c", "Makefile")]
         srcs.append(os.path.join(HERE, "..", "include", "usv_b200.h"))
         if _stale(ORACLE_SO, srcs):
             build()
@@ -54,6 +54,8 @@ def lib():
         L.usv_oracle_resolve_match_list.restype = C.c_int64
         L.usv_oracle_pair_nearest.restype = C.c_int64
         L.usv_oracle_id_matcher.restype = C.c_int64
+        L.usv_oracle_match_contours.restype = C.c_int64
+        L.usv_oracle_match_shapes_i1.restype = C.c_double
         _lib = L
     return _lib
 
@@ -239,3 +241,38 @@ def pair_nearest(t_left, t_right, max_dt):
     if n < 0:
         raise RuntimeError("pairing oracle failed")
     return ol[:n].copy(), orr[:n].copy()
+
+
+CONTOUR_DESC = np.dtype([("hu", "<f8", (7,)), ("area", "<f8")])
+
+
+def pack_contours(contours):
+    """list of [n_i, 2] int arrays -> (concatenated int32 xy, int32 offsets)"""
+    off = np.zeros(len(contours) + 1, np.int32)
+    for i, c in enumerate(contours):
+        off[i + 1] = off[i] + len(c)
+    pts = np.zeros((max(int(off[-1]), 1), 2), np.int32)
+    for i, c in enumerate(contours):
+        pts[off[i]:off[i + 1]] = np.asarray(c, np.int32).reshape(-1, 2)
+    return pts, off
+
+
+def contour_descriptor(contour):
+    c = np.ascontiguousarray(np.asarray(contour, np.int32).reshape(-1, 2))
+    d = np.zeros(1, CONTOUR_DESC)
+    lib().usv_oracle_contour_descriptor(_ptr(c), C.c_int32(len(c)), _ptr(d))
+    return d[0]
+
+
+def match_contours(contours_l, contours_r, threshold=0.75):
+    """GenerateMatchingList over contours (P/Main.cpp:403-426). Returns (matches, cost matrix)."""
+    pl, ol = pack_contours(contours_l)
+    pr, orr = pack_contours(contours_r)
+    nl, nr = len(contours_l), len(contours_r)
+    out = np.zeros(max(nl * nr, 1), _abi.MATCH_DTYPE)
+    cm = np.zeros((max(nl, 1), max(nr, 1)), np.float64)
+    n = lib().usv_oracle_match_contours(_ptr(pl), _ptr(ol), C.c_int32(nl), _ptr(pr), _ptr(orr), C.c_int32(nr), C.c_double(threshold),
+                                        _ptr(out), C.c_int64(len(out)), _ptr(cm))
+    if n < 0:
+        raise RuntimeError("contour oracle failed")
+    return out[:n], cm[:nl, :nr]

@@ -22,7 +22,7 @@ EXPORTS = (
     "usv_match_templates_host", "usv_disparity_to_distance", "usv_moving_object_distance",
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
     "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_wait",
-    "usv_stream_bytes_per_pair", "usv_probe_issue_rate",
+    "usv_stream_bytes_per_pair", "usv_probe_issue_rate", "usv_match_contours",
 )
 
 
@@ -207,6 +207,28 @@ class Context:
         self._check(lib().usv_coordinate_position(self._h, C.c_int32(int(camera_side)), _ptr(dist), _ptr(xy),
                                                   C.c_int64(len(dist)), _ptr(out)), "usv_coordinate_position")
         return out
+
+    def match_contours(self, contours_this, contours_other, accept_threshold=0.75):
+        """The reference's own GenerateMatchingList over contours (P/Main.cpp:403-426): lists of [n, 2] int
+        arrays -> (matches in i-major / j-minor order, full cost matrix)."""
+        def pack(cs):
+            off = np.zeros(len(cs) + 1, np.int32)
+            for i, c in enumerate(cs):
+                off[i + 1] = off[i] + len(c)
+            pts = np.zeros((max(int(off[-1]), 1), 2), np.int32)
+            for i, c in enumerate(cs):
+                pts[off[i]:off[i + 1]] = np.asarray(c, np.int32).reshape(-1, 2)
+            return pts, off
+        pl, ol = pack(contours_this)
+        pr, orr = pack(contours_other)
+        nl, nr = len(contours_this), len(contours_other)
+        out = np.zeros(max(nl * nr, 1), _abi.MATCH_DTYPE)
+        cm = np.zeros((max(nl, 1), max(nr, 1)), np.float64)
+        n = C.c_int64()
+        rc = lib().usv_match_contours(self._h, _ptr(pl), _ptr(ol), C.c_int32(nl), _ptr(pr), _ptr(orr), C.c_int32(nr),
+                                      C.c_double(accept_threshold), _ptr(out), C.c_int64(len(out)), C.byref(n), _ptr(cm))
+        self._check(rc, "usv_match_contours")
+        return out[:n.value], cm[:nl, :nr]
 
     def probe_issue_rate(self, which=0, target_ms=20.0):
         """Sustained thread-instructions/s of VABSDIFF4.U8.ACC (0) / IDP.4A (1): the ALU roofline denominator."""

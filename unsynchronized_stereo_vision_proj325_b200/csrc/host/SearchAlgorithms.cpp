@@ -35,6 +35,32 @@ static usv_frame_desc to_frame(const usv::ImageView& v) {
 
 const char* BlockSearchLastError() { return usv::thread_contexts().last_error.c_str(); }
 
+// P/Main.cpp:403-426, original arguments: the all-pairs shape + size cost runs in usv_contours.cu
+void GenerateMatchingList(std::vector<std::vector<cv::Point> > UsefulContoursL, std::vector<std::vector<cv::Point> > UsefulContoursR,
+                          std::vector<Match>& Matcher) {
+  if (UsefulContoursL.empty() || UsefulContoursR.empty()) return;  // :405
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  usv_ctx* ctx = tc.get(0);
+  if (!ctx) return;
+  auto pack = [](const std::vector<std::vector<cv::Point> >& cs, std::vector<int32_t>& pts, std::vector<int32_t>& off) {
+    off.assign(1, 0);
+    for (const auto& c : cs) {
+      for (const auto& p : c) { pts.push_back(p.x); pts.push_back(p.y); }
+      off.push_back((int32_t)(pts.size() / 2));
+    }
+    if (pts.empty()) pts.resize(2, 0);
+  };
+  std::vector<int32_t> pl, ol, pr, orr;
+  pack(UsefulContoursL, pl, ol);
+  pack(UsefulContoursR, pr, orr);
+  std::vector<usv_match> out(UsefulContoursL.size() * UsefulContoursR.size());
+  int64_t n = 0;
+  const int rc = usv_match_contours(ctx, pl.data(), ol.data(), (int32_t)UsefulContoursL.size(), pr.data(), orr.data(),
+                                    (int32_t)UsefulContoursR.size(), 0.75 /* :417 */, out.data(), (int64_t)out.size(), &n, nullptr);
+  if (!tc.check(ctx, rc, "usv_match_contours")) return;
+  for (int64_t k = 0; k < n; ++k) Matcher.push_back({out[k].LeftIndex, out[k].RightIndex, out[k].MatchValue});  // :418
+}
+
 void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView& OtherCamera, const BlockSearchSpec& Spec,
                           std::vector<Match>& Matcher, std::vector<double>* Distances) {
   usv::ThreadContexts& tc = usv::thread_contexts();

@@ -39,6 +39,22 @@ int main(int argc, char** argv) {
     CHECK(out.size() == 2 && out[0].LeftIndex == 0 && out[0].RightIndex == 1 && out[1].RightIndex == 1);
   }
 
+  // ---- the reference's original call (P/Main.cpp:1115-1117): contour lists in, Match list out
+  {
+    std::vector<std::vector<cv::Point> > Lc = {{{10, 10}, {60, 10}, {60, 40}, {10, 40}}, {{100, 100}, {130, 160}, {70, 160}}};
+    std::vector<std::vector<cv::Point> > Rc = {{{5, 12}, {54, 12}, {54, 43}, {5, 43}}, {{90, 100}, {121, 158}, {60, 161}}, {{0, 0}, {200, 0}, {200, 5}}};
+    std::vector<Match> Matcher, Tentative;
+    GenerateMatchingList(Lc, Rc, Matcher);
+    CHECK(Matcher.size() >= 2);
+    ResolveMatchList(Matcher, Tentative);
+    bool rect_ok = false, tri_ok = false;
+    for (const Match& m : Tentative) { rect_ok |= (m.LeftIndex == 0 && m.RightIndex == 0); tri_ok |= (m.LeftIndex == 1 && m.RightIndex == 1); }
+    CHECK(rect_ok && tri_ok);  // the rectangle pairs with the rectangle, the triangle with the triangle
+    std::vector<Match> none;
+    GenerateMatchingList(Lc, std::vector<std::vector<cv::Point> >(), none);
+    CHECK(none.empty());  // :405
+  }
+
   // ---- IDMatcher: the reference's join, comma-operator quirk included (P/Main.cpp:492)
   {
     std::vector<Match> cur = {{0, 5, .1}, {1, 7, .2}, {2, 5, .3}}, old = {{5, 9, .1}, {7, 3, .2}, {8, 1, .3}};

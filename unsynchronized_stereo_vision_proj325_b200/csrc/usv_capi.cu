@@ -17,6 +17,8 @@ namespace usv {
 cudaError_t launch_direct(const DevJob& J, int n_pairs, cudaStream_t st);
 // returns cudaErrorNotSupported when the dense kernels do not cover the job
 cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches);
+cudaError_t launch_contour_descriptors(const int* pts, const int* off, int n, double* desc, cudaStream_t st);
+cudaError_t launch_contour_costs(const double* dl, int nl, const double* dr, int nr, double* cost, cudaStream_t st);
 cudaError_t run_issue_probe(int which, int sms, double target_ms, double* lane_inst_per_s, uint32_t* d_scratch, cudaStream_t st);
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
 cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
@@ -439,6 +441,51 @@ extern "C" int usv_coordinate_position(usv_ctx* ctx, int32_t camera_side, const 
   ctx->launches++;
   CU(cudaMemcpyAsync(h_xyz, ctx->misc[2].p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return USV_OK;
+}
+
+// ---- the reference's original contour cost (matchShapes I1 + area ratio), P/Main.cpp:403-426 ----
+extern "C" int usv_match_contours(usv_ctx* ctx, const int32_t* pts_this, const int32_t* off_this, int32_t n_this,
+                                  const int32_t* pts_other, const int32_t* off_other, int32_t n_other, double accept_threshold,
+                                  usv_match* h_out, int64_t cap, int64_t* n_out, double* h_cost_matrix) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n_out) *n_out = 0;
+  if (n_this < 0 || n_other < 0 || cap < 0) return fail(ctx, USV_ERR_INVALID_ARG, "negative count");
+  if (n_this == 0 || n_other == 0) return USV_OK;  // P/Main.cpp:405
+  if (!pts_this || !off_this || !pts_other || !off_other || (cap > 0 && !h_out)) return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
+  for (int i = 0; i < n_this; ++i) if (off_this[i + 1] < off_this[i]) return fail(ctx, USV_ERR_INVALID_ARG, "offsets must ascend");
+  for (int i = 0; i < n_other; ++i) if (off_other[i + 1] < off_other[i]) return fail(ctx, USV_ERR_INVALID_ARG, "offsets must ascend");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  const size_t np_l = (size_t)off_this[n_this], np_r = (size_t)off_other[n_other];
+  if ((rc = up(ctx, ctx->misc[0], pts_this, sizeof(int32_t) * 2 * np_l))) return rc;
+  if ((rc = up(ctx, ctx->misc[1], off_this, sizeof(int32_t) * (n_this + 1)))) return rc;
+  if ((rc = up(ctx, ctx->misc[2], pts_other, sizeof(int32_t) * 2 * np_r))) return rc;
+  if ((rc = up(ctx, ctx->misc[3], off_other, sizeof(int32_t) * (n_other + 1)))) return rc;
+  if ((rc = grow(ctx, ctx->misc[4], sizeof(double) * 8 * n_this))) return rc;
+  if ((rc = grow(ctx, ctx->misc[5], sizeof(double) * 8 * n_other))) return rc;
+  const size_t n_pairs = (size_t)n_this * n_other;
+  if ((rc = grow(ctx, ctx->misc[6], sizeof(double) * n_pairs))) return rc;
+  CU(usv::launch_contour_descriptors((const int*)ctx->misc[0].p, (const int*)ctx->misc[1].p, n_this, (double*)ctx->misc[4].p, ctx->stream));
+  CU(usv::launch_contour_descriptors((const int*)ctx->misc[2].p, (const int*)ctx->misc[3].p, n_other, (double*)ctx->misc[5].p, ctx->stream));
+  CU(usv::launch_contour_costs((const double*)ctx->misc[4].p, n_this, (const double*)ctx->misc[5].p, n_other, (double*)ctx->misc[6].p, ctx->stream));
+  ctx->launches += 3;
+  ctx->last_kernel = "contour_cost_kernel";
+  std::vector<double> cost(n_pairs);
+  CU(cudaMemcpyAsync(cost.data(), ctx->misc[6].p, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (h_cost_matrix) memcpy(h_cost_matrix, cost.data(), sizeof(double) * n_pairs);
+  int64_t n = 0;
+  for (int i = 0; i < n_this; ++i)      // i-major (P/Main.cpp:408)
+    for (int j = 0; j < n_other; ++j) { // j-minor (P/Main.cpp:410)
+      const double v = cost[(size_t)i * n_other + j];
+      if (v < accept_threshold) {       // Is it at least a partial match? (P/Main.cpp:417); NaN never passes
+        if (n >= cap) return fail(ctx, USV_ERR_INVALID_ARG, "output capacity %lld too small", (long long)cap);
+        h_out[n].LeftIndex = (uint32_t)i; h_out[n].RightIndex = (uint32_t)j; h_out[n].MatchValue = v;
+        ++n;
+      }
+    }
+  if (n_out) *n_out = n;
   return USV_OK;
 }
 
