@@ -24,7 +24,8 @@ CASES = _golden_cases()
 
 
 def test_golden_files_present():
-    assert sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))) == sorted(CASES)
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    assert [n for n in names if n != "contours_cv2"] == sorted(CASES)  # contours_cv2: tests/test_contours.py
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
