@@ -31,6 +31,8 @@
 // lanes/clk/SM on the ALU pipe, IMAD at 64 lanes/clk/SM on the FMA pipe in parallel,
 // VIMNMX at 128. The old-row subtraction and the key slide are IMADs on purpose, to keep
 // them off the ALU pipe that bounds this kernel.
+#include <type_traits>
+
 #include "usv_common.cuh"
 
 namespace usv {
@@ -104,49 +106,38 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
     }
   }
 
-  // ---- staging roles: thread t < 32 stages L word t, 32 <= t < 32 + kRW stages R word t - 32, for all
-  // four byte-shifted copies (one pair of aligned global words -> 3 funnel shifts -> 4 STS)
-  const bool stager = tid < kLW + kRW;
-  const bool st_left = tid < kLW;
-  const int st_w = st_left ? tid : tid - kLW;
+  // ---- staging: a block of kRB rows is 18 chunks of 4 words per row (8 of the L segment, 10 of the R
+  // segment); thread t < 18 * kRB takes chunk t % 18 of row t / 18: five aligned global words -> 12 funnel
+  // shifts -> the four byte-shifted copies, one STS.128 each
+  constexpr int kChunks = kLW / 4 + 10;
+  const bool stager = tid < kChunks * kRB;
+  const int st_row = tid / kChunks, st_c = tid - st_row * kChunks;
+  const bool st_left = st_c < kLW / 4;
+  const int st_w = st_left ? 4 * st_c : 4 * (st_c - kLW / 4);
   const int st_kw = st_left ? kLW : kRW;
   const int st_off = (st_left ? 0 : 4 * kLW) + st_w;
-  const uint32_t* st_g = st_left ? Lg : Rg;
-  int g0, g1;
-  {
-    const int gb = ((st_left ? X0 : XR0) >> 2) + st_w;  // X0, XR0 are multiples of 4
-    g0 = min(max(gb, 0), row_words - 1);
-    g1 = min(max(gb + 1, 0), row_words - 1);
-  }
-  int stage_slot = 0;  // ring slot of the next row to stage (calls come in row order, kRB rows apart)
-  auto stage = [&](int row_begin) {
-    const int nrows = min(kRB, rows_in - row_begin);
-    if (!stager || nrows <= 0) return;
-    uint32_t a[kRB], b[kRB];
-    const uint32_t* gp = st_g + (long long)row_begin * row_words;
+  const uint32_t* st_g = (st_left ? Lg : Rg) + (long long)st_row * row_words;
+  int gi[5];
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) {
-      if (r < nrows) { a[r] = __ldg(gp + g0); b[r] = __ldg(gp + g1); gp += row_words; }
+  for (int k = 0; k < 5; ++k) gi[k] = min(max(((st_left ? X0 : XR0) >> 2) + st_w + k, 0), row_words - 1);  // X0, XR0 are multiples of 4
+  int stage_slot = st_row;  // ring slot of this thread's row in the next block to stage
+  auto stage = [&](int row_begin) {
+    if (stager && row_begin + st_row < rows_in) {
+      const uint32_t* gp = st_g + (long long)row_begin * row_words;
+      uint32_t w[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) w[k] = __ldg(gp + gi[k]);
+      uint32_t* dst = s_ring + (size_t)stage_slot * kRowWords + st_off;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int c = 1; c < 4; ++c)
+        *reinterpret_cast<uint4*>(dst + c * st_kw) =
+            make_uint4(__funnelshift_r(w[0], w[1], 8 * c), __funnelshift_r(w[1], w[2], 8 * c),
+                       __funnelshift_r(w[2], w[3], 8 * c), __funnelshift_r(w[3], w[4], 8 * c));
     }
-    int slot = stage_slot;
     stage_slot += kRB;
     if (stage_slot >= nr) stage_slot -= nr;
-#pragma unroll
-    for (int r = 0; r < kRB; ++r) {
-      if (r < nrows) {
-        uint32_t* dst = s_ring + (size_t)slot * kRowWords + st_off;
-        dst[0] = a[r];
-        dst[st_kw] = __funnelshift_r(a[r], b[r], 8);
-        dst[2 * st_kw] = __funnelshift_r(a[r], b[r], 16);
-        dst[3 * st_kw] = __funnelshift_r(a[r], b[r], 24);
-        slot = slot + 1 == nr ? 0 : slot + 1;
-      }
-    }
   };
-
-  __syncthreads();  // previous pass done with the ring; s_best init visible
-  stage(0);
-  __syncthreads();
 
   // this thread's operand words inside a ring row: L words [8ul, 8ul+8) of copy p; R words
   // [rbase, rbase+12) of copy q, element (i, j) at rbase + (DIR<0 ? i - j + 4 : i + j)
@@ -158,97 +149,117 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   uint32_t* my_best = s_best + p * 32 + 8 * ul + own_i;
 
   int slot_new = 0, slot_old = 0;
-  const int n_blk = (rows_in + kRB - 1) / kRB;
-  for (int blk = 0; blk < n_blk; ++blk) {
-    stage((blk + 1) * kRB);  // ring depth >= th + 2*kRB keeps every row this block still needs intact
-    const int r_end = min(rows_in, (blk + 1) * kRB);
-    for (int row = blk * kRB; row < r_end; ++row) {
-      // all shared loads of this row up front (the old-row slot is harmless garbage while row < th)
+
+  // one row of the band: the row enters the windows (V += h), the row th above leaves them (V -= h), the
+  // window sums become keys and are folded into the running best. The three phases of a pass (warm-up,
+  // first full window, steady state) are separate straight-line instantiations, so that the steady-state
+  // body is one basic block the scheduler can interleave across the ALU and FMA pipes.
+  auto row_body = [&](auto has_old_t, auto has_keys_t, int row) {
+    constexpr bool HAS_OLD = decltype(has_old_t)::value, HAS_KEYS = decltype(has_keys_t)::value;
+    {
       const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot_new * kRowWords);
       const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_new * kRowWords);
+      const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
+      slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
+      const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+      const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
+    }
+    if (HAS_OLD) {
       const uint4* lo = reinterpret_cast<const uint4*>(my_l + (size_t)slot_old * kRowWords);
       const uint4* ro = reinterpret_cast<const uint4*>(my_r + (size_t)slot_old * kRowWords);
-      const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
       const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
-      slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
-      // ---- new row enters the window
-      {
-        const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+      slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
+      const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
-      }
-      // ---- old row leaves the window
-      if (row >= th) {
-        const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
-            V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
-          }
-        slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
-      }
-      // ---- window sums, keys, running min
-      if (row >= th - 1) {
-        uint32_t best[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) best[i] = 0xffffffffu;
-#pragma unroll
-        for (int jp = 0; jp < 4; jp += 2) {
-          uint32_t key[2][8];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int j = jp + jj;
-            // columns 8 .. 8+NW-2 come from the next u-lane (garbage for ul = 3: those positions are not emitted)
-            uint32_t Vx[8 + NW - 1];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) Vx[i] = V[i][j];
-#pragma unroll
-            for (int c = 0; c < NW - 1; ++c) Vx[8 + c] = __shfl_down_sync(0xffffffffu, V[c][j], 1, 4);
-            uint32_t T = Vx[0];
-#pragma unroll
-            for (int k = 1; k < NW; ++k) T += Vx[k];
-            // slide the packed key itself: key_{i+1} = key_i + (Vx[i+NW] - Vx[i]) << xb, two IMADs on the
-            // FMA pipe (wrap-around arithmetic is exact: every true key fits in 31 bits, BIG adds bit 31)
-            uint32_t k = imad_u32(T, key_scale, code[j]);
-            key[jj][0] = k;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-              k = imad_u32(Vx[i], minus_scale, k);
-              k = imad_u32(Vx[i + NW], key_scale, k);
-              key[jj][i + 1] = k;
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) best[i] = __vimin3_u32(best[i], key[0][i], key[1][i]);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
+          V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
         }
-        // reduce-scatter min over the 8 d-lanes (lane bits 4, 3, 2): 4 + 2 + 1 shuffles, each lane ends
-        // with the minimum of one window
-        uint32_t h4[4], h2[2], h1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t keep = b4 ? best[4 + k] : best[k], send = b4 ? best[k] : best[4 + k];
-          h4[k] = min(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint32_t keep = b3 ? h4[2 + k] : h4[k], send = b3 ? h4[k] : h4[2 + k];
-          h2[k] = min(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-        }
-        {
-          const uint32_t keep = b2 ? h2[1] : h2[0], send = b2 ? h2[0] : h2[1];
-          h1 = min(keep, __shfl_xor_sync(0xffffffffu, send, 4));
-        }
-        uint32_t* bp = my_best + (size_t)(row - (th - 1)) * 128;
-        *bp = min(*bp, h1);
-      }
     }
-    __syncthreads();
+    if (HAS_KEYS) {
+      uint32_t best[8];
+#pragma unroll
+      for (int jp = 0; jp < 4; jp += 2) {
+        uint32_t key[2][8];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = jp + jj;
+          // columns 8 .. 8+NW-2 come from the next u-lane (garbage for ul = 3: those positions are not emitted)
+          uint32_t Vx[8 + NW - 1];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) Vx[i] = V[i][j];
+#pragma unroll
+          for (int c = 0; c < NW - 1; ++c) Vx[8 + c] = __shfl_down_sync(0xffffffffu, V[c][j], 1, 4);
+          uint32_t T = Vx[0];
+#pragma unroll
+          for (int k = 1; k < NW; ++k) T += Vx[k];
+          // slide the packed key itself: key_{i+1} = key_i + (Vx[i+NW] - Vx[i]) << xb, two IMADs on the
+          // FMA pipe (wrap-around arithmetic is exact: every true key fits in 31 bits, BIG adds bit 31)
+          uint32_t k = imad_u32(T, key_scale, code[j]);
+          key[jj][0] = k;
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            k = imad_u32(Vx[i], minus_scale, k);
+            k = imad_u32(Vx[i + NW], key_scale, k);
+            key[jj][i + 1] = k;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = jp == 0 ? min(key[0][i], key[1][i]) : __vimin3_u32(best[i], key[0][i], key[1][i]);
+      }
+      // reduce-scatter min over the 8 d-lanes (lane bits 4, 3, 2): 4 + 2 + 1 shuffles, each lane ends
+      // with the minimum of one window
+      uint32_t h4[4], h2[2], h1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t keep = b4 ? best[4 + k] : best[k], send = b4 ? best[k] : best[4 + k];
+        h4[k] = min(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint32_t keep = b3 ? h4[2 + k] : h4[k], send = b3 ? h4[k] : h4[2 + k];
+        h2[k] = min(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+      }
+      {
+        const uint32_t keep = b2 ? h2[1] : h2[0], send = b2 ? h2[0] : h2[1];
+        h1 = min(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+      }
+      uint32_t* bp = my_best + (size_t)(row - (th - 1)) * 128;
+      *bp = min(*bp, h1);
+    }
+  };
+  // every kRB rows: all warps are done with the previous block (its oldest ring rows may be overwritten), the
+  // block staged meanwhile becomes visible, and the block after it is fetched
+  auto block_edge = [&](int row) {
+    if ((row & (kRB - 1)) == 0) {
+      __syncthreads();
+      stage(row + kRB);
+    }
+  };
+
+  __syncthreads();  // previous pass done with the ring; s_best init visible
+  stage(0);
+  int row = 0;
+  const int warm = min(th - 1, rows_in);
+  for (; row < warm; ++row) {
+    block_edge(row);
+    row_body(std::false_type{}, std::false_type{}, row);
+  }
+  if (row < rows_in) {
+    block_edge(row);
+    row_body(std::false_type{}, std::true_type{}, row);
+    ++row;
+  }
+  for (; row < rows_in; ++row) {
+    block_edge(row);
+    row_body(std::true_type{}, std::true_type{}, row);
   }
 }
 
