@@ -71,13 +71,17 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // i0-1, i0-1-NW, ... and i1+NW-1, i1+2NW-1, ... start at BIG = 2^(31-xb) instead of 0. Every invalid
 // window then contains exactly one BIG column and its key carries bit 31 (true keys stay below 2^31,
 // checked on the host), every valid window contains none. No per-element masks, no second code path.
-template <int DIR, int NW>
+template <int DIR, int NW, bool FOLD>
 __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
                                            const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
-                                           const int XR0, const int x0, const int dbase, const int rows_in,
-                                           const uint32_t minus_one) {
+                                           const int XR0, const int run, const int dbase, const int r_shift,
+                                           const int rows_in, const uint32_t minus_one) {
+  // `run` is the 32-px x-run this lane works on: its own (lane & 3), or run 3 of a later pass for the guest lane
+  // of a folded pass (see the kernel); `r_shift` moves the guest's R operands to that pass's disparities
   const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
-  const int ul = lane & 3, dl = lane >> 2, q = dl & 3, jh = dl >> 2;
+  const int ul = run, dl = lane >> 2, q = dl & 3, jh = dl >> 2;
+  const int x0 = X0 + p + 32 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i, i < 8)
+  const bool guest = FOLD && (lane & 3) == 0;
   const int th = J.th, nr = cfg.nr;
   const int row_words = J.row_stride >> 2;
   const uint32_t key_scale = 1u << cfg.xb;
@@ -142,7 +146,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   // this thread's operand words inside a ring row: L words [8ul, 8ul+8) of copy p; R words
   // [rbase, rbase+12) of copy q, element (i, j) at rbase + (DIR<0 ? i - j + 4 : i + j)
   const uint32_t* my_l = s_ring + p * kLW + 8 * ul;
-  const uint32_t* my_r = s_ring + 4 * kLW + q * kRW + 8 * ul + (DIR < 0 ? 4 - 4 * jh : 4 * jh);
+  const uint32_t* my_r = s_ring + 4 * kLW + q * kRW + 8 * ul + (DIR < 0 ? 4 - 4 * jh : 4 * jh) + r_shift;
   // the window this lane owns after the reduce-scatter min: position 8*ul + own_i
   const int own_i = ((dl >> 2) & 1) * 4 + ((dl >> 1) & 1) * 2 + (dl & 1);
   const bool b4 = (dl >> 2) & 1, b3 = (dl >> 1) & 1, b2 = dl & 1;
@@ -232,7 +236,11 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
         h1 = min(keep, __shfl_xor_sync(0xffffffffu, send, 4));
       }
       uint32_t* bp = my_best + (size_t)(row - (th - 1)) * 128;
-      *bp = min(*bp, h1);
+      if (!guest) *bp = min(*bp, h1);
+      if (FOLD) {  // the guest lane shares its windows with lane 3 of the same d-lane: merge after it
+        __syncwarp();
+        if (guest) *bp = min(*bp, h1);
+      }
     }
   };
   // every kRB rows: all warps are done with the previous block (its oldest ring rows may be overwritten), the
@@ -279,7 +287,6 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
   const int rows_in = bh + J.th - 1;
-  const int x0 = X0 + p + 32 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i, i < 8)
   const uint32_t* Lg = reinterpret_cast<const uint32_t*>(J.left + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
   const uint32_t* Rg = reinterpret_cast<const uint32_t*>(J.right + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
   const int xb = cfg.xb;
@@ -294,15 +301,38 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   d_lo = d_lo & ~3;  // floor to a multiple of 4 (also for negatives): keeps the R copies word aligned
   // warp p, d-lane (jh, q) covers d = D0 + 16jh + 4j + (p - q) [LeftCam] / ... + (q - p) [RightCam], j < 4:
   // every warp sees 32 consecutive d starting in [D0 - 3, D0]; the shortest reach is D0 + 28.
-  const int n_pass = d_hi >= d_lo ? (d_hi - d_lo + 3) / 32 + 1 : 0;
+  // Passes each 32-px x-run (x-lane) needs. LeftCam runs further right reach further (d <= x): the last passes
+  // of a tile keep only runs {1,2,3}, {2,3}, {3} busy.
+  int n_run[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int xl = max(X0 + 32 * r, 0), xh = min(min(X0 + 32 * r + 31, X0 + cfg.stride_px - 1), J.nxc - 1);
+    int dh;
+    if (DIR < 0) dh = min(J.dmax, xh); else dh = min(J.dmax, J.nxc - 1 - xl);
+    n_run[r] = (xh >= xl && dh >= d_lo) ? (dh - d_lo + 3) / 32 + 1 : 0;
+  }
+  const int n_all = max(max(n_run[0], n_run[1]), max(n_run[2], n_run[3]));
+  // Fold (LeftCam): run 3 never uses its neighbour's columns (the tile's last 3 positions are not emitted), so
+  // its lane-0 slot in a pass where run 0 is already done can host run 3 of one of the tile's last passes,
+  // which then need not run at all.
+  int n_fold = 0;
+  if (DIR < 0 && n_run[0] <= n_run[1] && n_run[1] <= n_run[2] && n_run[2] <= n_run[3] && n_run[3] - n_run[0] <= 3)
+    n_fold = min(n_run[1] - n_run[0], n_run[3] - n_run[2]);
+  const int n_pass = n_all - n_fold;
 
   for (int pass = 0; pass < n_pass; ++pass) {
     const int D0 = d_lo + 32 * pass;
+    const bool fold_pass = pass >= n_run[0] && pass < n_run[0] + n_fold;
+    const bool guest = fold_pass && ul == 0;
+    const int run = guest ? 3 : ul;
+    const int D0_mine = guest ? d_lo + 32 * (n_all - 1 - (pass - n_run[0])) : D0;
     // d of (this lane, j = 0); d_j = dbase + 4j, j < 4. dl = 4*jh + q: R copy q, upper/lower half of the 8 d-steps
-    const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
+    const int dbase = D0_mine + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
     // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
-    dense_pass<DIR, NW>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, x0, dbase, rows_in, minus_one);
+    const int r_shift = DIR < 0 ? -((D0_mine - D0) >> 2) : ((D0_mine - D0) >> 2);
+    if (fold_pass) dense_pass<DIR, NW, true>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    else dense_pass<DIR, NW, false>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
   }
   __syncthreads();
 
