@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define USV_ABI_VERSION 1
+#define USV_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------ */
 #define USV_OK 0
@@ -111,6 +111,9 @@ typedef struct usv_outputs {
   double *distance;        /* cm, f64 (reference type)                        */
   float *distance_f32;     /* cm, f32 copy for bandwidth-bound consumers      */
   uint16_t *disparity_u16; /* d of the winner or USV_NO_DISPARITY             */
+  uint16_t *raw_cost_u16;  /* raw_cost as u16 (0xFFFF = no candidate): SAD only,
+                              and only when 255*tmpl_w*tmpl_h*channels fits 16
+                              bits (else USV_ERR_UNSUPPORTED); lossless        */
 } usv_outputs;
 
 typedef struct usv_ctx usv_ctx;       /* one per (GPU, host thread)          */
@@ -228,6 +231,7 @@ int64_t usv_pair_nearest(const double *t_left, int64_t n_left,
 #define USV_OUT_DISTANCE 0x10
 #define USV_OUT_DISTANCE_F32 0x20
 #define USV_OUT_DISPARITY_U16 0x40
+#define USV_OUT_RAW_COST_U16 0x80
 
 int usv_stream_create(usv_ctx *ctx, const usv_frame_desc *frame,
                       const usv_search_params *params, int32_t pairs_per_slot,

@@ -97,6 +97,17 @@ def alloc_outputs(n, mask):
 ALL_OUTPUTS = 0x7F
 
 
+def _with_cost_u16(arrs, mask, had_raw):
+    """raw_cost_u16 (include/usv_b200.h): the u32 cost narrowed to 16 bits; ~0 (no candidate) becomes 0xFFFF."""
+    if mask & _abi.OUT_RAW_COST_U16:
+        rc = arrs["raw_cost"]
+        assert (rc[rc != 0xFFFFFFFF] <= 0xFFFF).all(), "raw_cost_u16 requested for costs that do not fit"
+        arrs["raw_cost_u16"] = rc.astype(np.uint16)
+        if not had_raw:
+            del arrs["raw_cost"]
+    return arrs
+
+
 def grid_dims(frame, params):
     nx, ny, ev = C.c_int32(), C.c_int32(), C.c_int64()
     rc = lib().usv_oracle_grid_dims(C.byref(frame), C.byref(params), C.byref(nx), C.byref(ny), C.byref(ev))
@@ -111,10 +122,11 @@ def match_dense(left, right, params, mask=ALL_OUTPUTS, threads=0):
     f = _abi.frame_desc_for(left)
     nx, ny, _ = grid_dims(f, params)
     n = left.shape[0]
-    arrs, st = alloc_outputs(n * nx * ny, mask)
+    arrs, st = alloc_outputs(n * nx * ny, (mask & ~_abi.OUT_RAW_COST_U16) | (_abi.OUT_RAW_COST if mask & _abi.OUT_RAW_COST_U16 else 0))
     rc = lib().usv_oracle_match_dense(_ptr(left), _ptr(right), C.byref(f), C.c_int32(n), C.byref(params), C.byref(st), C.c_int32(threads))
     if rc:
         raise RuntimeError("oracle match_dense failed")
+    arrs = _with_cost_u16(arrs, mask, bool(mask & _abi.OUT_RAW_COST))
     return {k: v.reshape(n, ny * nx) for k, v in arrs.items()}
 
 

@@ -231,3 +231,23 @@ def test_stream_matches_oracle(ctx, oracle):
         assert np.allclose(st.slots[s0]["out"]["distance_f32"][: b0 - a0], exp["distance_f32"][a0:b0], rtol=1e-6)
     assert st.h2d_bytes_per_pair == 2 * 256 * h and st.d2h_bytes_per_pair == (4 + 4 + 4 + 2) * st.nx * st.ny
     st.close()
+
+
+@pytest.mark.gpu
+def test_raw_cost_u16_is_lossless_or_refused(ctx, oracle):
+    """raw_cost_u16 (include/usv_b200.h): same costs as raw_cost for templates whose SAD fits 16 bits, 0xFFFF for
+    windows without candidates, USV_ERR_UNSUPPORTED otherwise."""
+    left, right = synth.make_pairs(2, 200, 40, 1, shift=9, noise_sigma=2.0, seed=5)
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad", search_min=3, search_max=40)
+    mask = _abi.OUT_RAW_COST | _abi.OUT_RAW_COST_U16 | _abi.OUT_DISPARITY_U16
+    got = ctx.match_dense(left, right, p, mask=mask)
+    exp = oracle.match_dense(left, right, p, mask=mask)
+    assert np.array_equal(got["raw_cost_u16"], exp["raw_cost_u16"])
+    assert np.array_equal(got["raw_cost_u16"], got["raw_cost"].astype(np.uint16))
+    assert (got["raw_cost_u16"][:, :3] == 0xFFFF).all()  # x < search_min: no candidate
+    big = _abi.make_params(tmpl_w=32, tmpl_h=32, cost="sad", search_max=40)
+    with pytest.raises(api.UsvError):
+        ctx.match_dense(left, right, big, mask=_abi.OUT_RAW_COST_U16)
+    ssd = _abi.make_params(tmpl_w=8, tmpl_h=8, cost="ssd", search_max=40)
+    with pytest.raises(api.UsvError):
+        ctx.match_dense(left, right, ssd, mask=_abi.OUT_RAW_COST_U16)

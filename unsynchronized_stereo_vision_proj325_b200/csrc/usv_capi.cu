@@ -46,10 +46,11 @@ struct usv_ctx {
   double* lut[3] = {nullptr, nullptr, nullptr};
   int lut_n[3] = {0, 0, 0};
   // grow-only scratch for the host paths
-  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[7], misc[8];
+  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8];
 };
 
-static const size_t kOutElem[7] = {sizeof(usv_match), 4, 4, 8, 8, 4, 2};
+static const int kNumOut = 8;
+static const size_t kOutElem[kNumOut] = {sizeof(usv_match), 4, 4, 8, 8, 4, 2, 2};
 
 static int fail(usv_ctx* c, int code, const char* fmt, ...) {
   if (c) {
@@ -85,7 +86,8 @@ static void** out_slot(usv_outputs* o, int i) {
     case 3: return (void**)&o->score;
     case 4: return (void**)&o->distance;
     case 5: return (void**)&o->distance_f32;
-    default: return (void**)&o->disparity_u16;
+    case 6: return (void**)&o->disparity_u16;
+    default: return (void**)&o->raw_cost_u16;
   }
 }
 
@@ -112,6 +114,13 @@ static int check_common(usv_ctx* ctx, const usv_frame_desc* f, const usv_search_
   if (p->distance_kind < USV_DIST_NONE || p->distance_kind > USV_DIST_POWERLAW)
     return fail(ctx, USV_ERR_INVALID_ARG, "unknown distance_kind %d", p->distance_kind);
   if (p->camera_side != USV_LEFT_CAM && p->camera_side != USV_RIGHT_CAM) return fail(ctx, USV_ERR_INVALID_ARG, "camera_side must be 0 or 1");
+  return USV_OK;
+}
+
+// raw_cost_u16 is lossless or refused: every SAD of the template must fit 16 bits
+static int check_cost_u16(usv_ctx* ctx, const usv_frame_desc* f, const usv_search_params* p) {
+  if (p->cost_kind != USV_COST_SAD || 255ll * p->tmpl_w * p->tmpl_h * f->channels > 0xFFFFll)
+    return fail(ctx, USV_ERR_UNSUPPORTED, "raw_cost_u16 needs SAD with 255*tmpl_w*tmpl_h*channels <= 65535");
   return USV_OK;
 }
 
@@ -218,6 +227,7 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
   if (!d_left || !d_right || !d_out) return fail(ctx, USV_ERR_INVALID_ARG, "null device pointer");
   if (!aligned16(d_left) || !aligned16(d_right) || (f->row_stride & 15) || (f->frame_stride & 15))
     return fail(ctx, USV_ERR_INVALID_ARG, "device frames need 16-byte aligned base, row_stride and frame_stride");
+  if (d_out->raw_cost_u16 && (rc = check_cost_u16(ctx, f, p))) return rc;
   if (n_pairs == 0) return USV_OK;
   CU(cudaSetDevice(ctx->device));
   DevJob J;
@@ -320,7 +330,7 @@ static int match_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_righ
   usv_outputs d_out;
   memset(&d_out, 0, sizeof(d_out));
   usv_outputs ho = *h_out;
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < kNumOut; ++i) {
     if (*out_slot(&ho, i)) {
       if ((rc = grow(ctx, ctx->out[i], kOutElem[i] * n_res))) return rc;
       *out_slot(&d_out, i) = ctx->out[i].p;
@@ -349,7 +359,7 @@ static int match_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_righ
   rc = match_device(ctx, (const uint8_t*)ctx->in_l.p, (const uint8_t*)ctx->in_r.p, &df, n_pairs, p, &d_out, d_tx, d_ty, n_templates,
                     d_rows, d_srows, row_cap, st);
   if (rc) return rc;
-  for (int i = 0; i < 7; ++i)
+  for (int i = 0; i < kNumOut; ++i)
     if (*out_slot(&ho, i)) CU(cudaMemcpyAsync(*out_slot(&ho, i), ctx->out[i].p, kOutElem[i] * n_res, cudaMemcpyDeviceToHost, st));
   if (d_rows) CU(cudaMemcpyAsync(h_cost_rows, d_rows, sizeof(uint32_t) * n_res * row_cap, cudaMemcpyDeviceToHost, st));
   if (d_srows) CU(cudaMemcpyAsync(h_score_rows, d_srows, sizeof(double) * n_res * row_cap, cudaMemcpyDeviceToHost, st));
@@ -573,7 +583,7 @@ extern "C" int usv_stream_destroy(usv_stream* s) {
     if (sl.h_r) cudaFreeHost(sl.h_r);
     if (sl.d_l) cudaFree(sl.d_l);
     if (sl.d_r) cudaFree(sl.d_r);
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < kNumOut; ++i) {
       if (*out_slot(&sl.h_out, i)) cudaFreeHost(*out_slot(&sl.h_out, i));
       if (*out_slot(&sl.d_out, i)) cudaFree(*out_slot(&sl.d_out, i));
     }
@@ -591,6 +601,7 @@ extern "C" int usv_stream_create(usv_ctx* ctx, const usv_frame_desc* frame, cons
   if (pairs_per_slot <= 0 || n_slots <= 0 || n_slots > 64) return fail(ctx, USV_ERR_INVALID_ARG, "bad slot geometry");
   int rc = check_common(ctx, frame, params, pairs_per_slot);
   if (rc) return rc;
+  if ((output_mask & USV_OUT_RAW_COST_U16) && (rc = check_cost_u16(ctx, frame, params))) return rc;
   int32_t nx, ny;
   if (usv_grid_dims(frame, params, &nx, &ny, nullptr)) return fail(ctx, USV_ERR_INVALID_ARG, "bad geometry");
   CU(cudaSetDevice(ctx->device));
@@ -618,7 +629,7 @@ extern "C" int usv_stream_create(usv_ctx* ctx, const usv_frame_desc* frame, cons
     if ((e = cudaMalloc((void**)&sl.d_r, fbytes)) != cudaSuccess) break;
     memset(sl.h_l, 0, fbytes);
     memset(sl.h_r, 0, fbytes);
-    for (int i = 0; i < 7 && e == cudaSuccess; ++i) {
+    for (int i = 0; i < kNumOut && e == cudaSuccess; ++i) {
       if (!(output_mask & (1u << i))) continue;
       if ((e = cudaHostAlloc(out_slot(&sl.h_out, i), kOutElem[i] * n_res, cudaHostAllocDefault)) != cudaSuccess) break;
       e = cudaMalloc(out_slot(&sl.d_out, i), kOutElem[i] * n_res);
@@ -661,7 +672,7 @@ extern "C" int usv_stream_submit(usv_stream* s, int32_t slot, int32_t n_pairs) {
     int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
     if (rc) return rc;
     const size_t n_res = (size_t)s->n_win * n_pairs;
-    for (int i = 0; i < 7; ++i)
+    for (int i = 0; i < kNumOut; ++i)
       if (*out_slot(&sl.h_out, i))
         CU(cudaMemcpyAsync(*out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res, cudaMemcpyDeviceToHost, sl.st));
   }
@@ -699,7 +710,7 @@ extern "C" int usv_stream_submit_from(usv_stream* s, int32_t slot, const uint8_t
     int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
     if (rc) return rc;
     const size_t n_res = (size_t)s->n_win * n_pairs;
-    for (int i = 0; i < 7; ++i)
+    for (int i = 0; i < kNumOut; ++i)
       if (*out_slot(&sl.h_out, i))
         CU(cudaMemcpyAsync(*out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res, cudaMemcpyDeviceToHost, sl.st));
   }
@@ -718,7 +729,7 @@ extern "C" int usv_stream_bytes_per_pair(const usv_stream* s, int64_t* h2d, int6
   if (!s) return USV_ERR_INVALID_ARG;
   if (h2d) *h2d = 2 * s->hf.frame_stride;
   int64_t o = 0;
-  for (int i = 0; i < 7; ++i)
+  for (int i = 0; i < kNumOut; ++i)
     if (s->mask & (1u << i)) o += (int64_t)kOutElem[i] * s->n_win;
   if (d2h) *d2h = o;
   return USV_OK;

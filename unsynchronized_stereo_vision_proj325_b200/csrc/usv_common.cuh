@@ -98,6 +98,7 @@ __device__ inline void write_result(const DevJob& J, long long g, uint32_t left_
   }
   if (J.out.right_index) J.out.right_index[g] = rindex;
   if (J.out.raw_cost) J.out.raw_cost[g] = raw;
+  if (J.out.raw_cost_u16) J.out.raw_cost_u16[g] = (uint16_t)raw;  // host checked that every cost fits; ~0 -> 0xFFFF
   if (J.out.score) J.out.score[g] = score;
   if (J.out.distance) J.out.distance[g] = dist;
   if (J.out.distance_f32) J.out.distance_f32[g] = (float)dist;
