@@ -17,6 +17,7 @@
  *   usv_search_params.accept_*     -> `DMatchValue < 0.75` accept test  P/Main.cpp:417
  *   distance_kind PINHOLE          -> inline disparity + pinhole        P/Main.cpp:681-694
  *   distance_kind POWERLAW         -> power-law fit                     P/DistanceCalculator.cpp:84
+ *   usv_resolve_match_list         -> ResolveMatchList (whole list)     P/Main.cpp:432-477
  *   usv_moving_object_distance     -> MovingObjectDistanceCalculator    P/DistanceCalculator.cpp:15-88
  *   usv_coordinate_position        -> CooridinatePositionCalculator     P/DistanceCalculator.cpp:90-141
  *   usv_pair_nearest / usv_stream_*-> CameraThread capture + timestamps P/Main.cpp:876-905
@@ -180,6 +181,21 @@ int usv_match_contours(usv_ctx *ctx, const int32_t *pts_this,
                        int32_t n_other, double accept_threshold,
                        usv_match *h_out, int64_t cap, int64_t *n_out,
                        double *h_cost_matrix);
+
+/* ---- ResolveMatchList, P/Main.cpp:432-477, on the GPU for lists of any length ----
+ * One greedy pass in list order: a match overwrites every earlier tentative entry that shares LeftIndex
+ * or RightIndex (:450) and is strictly worse (:451); if it overwrote nothing it is appended (:463-466).
+ * Output = the reference's TentativeMatch, duplicates and all. Returns the full output length in *n_out
+ * even when it exceeds cap (only the first cap records are written).
+ * skip_unmatched != 0: records with RightIndex == USV_NO_MATCH (windows without an accepted candidate,
+ * as the dense kernels write them) are dropped first, as the C++ wrapper does before resolving. */
+int usv_resolve_match_list(usv_ctx *ctx, const usv_match *h_in, int64_t n,
+                           int32_t skip_unmatched, usv_match *h_out, int64_t cap,
+                           int64_t *n_out);
+/* Device pointers (d_n_out: one int64 in device memory); enqueued on cuda_stream. */
+int usv_resolve_match_list_device(usv_ctx *ctx, const usv_match *d_in, int64_t n,
+                                  int32_t skip_unmatched, usv_match *d_out,
+                                  int64_t cap, int64_t *d_n_out, void *cuda_stream);
 
 /* ---- distance family (host buffers; one tiny kernel each) ---------------- */
 int usv_disparity_to_distance(usv_ctx *ctx, const int32_t *h_disp, int64_t n,

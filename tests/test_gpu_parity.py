@@ -251,3 +251,62 @@ def test_raw_cost_u16_is_lossless_or_refused(ctx, oracle):
     ssd = _abi.make_params(tmpl_w=8, tmpl_h=8, cost="ssd", search_max=40)
     with pytest.raises(api.UsvError):
         ctx.match_dense(left, right, ssd, mask=_abi.OUT_RAW_COST_U16)
+
+
+# ---- ResolveMatchList on the GPU (usv_resolve.cu) against the restatement and the reference's own lines ----------
+RESOLVE_KAT = [  # produced by running P/Main.cpp:432-477 itself
+    ([(0, 0, .5), (0, 1, .3), (0, 2, .4), (0, 3, .1), (0, 4, .2)], [(0, 3, .1), (0, 3, .1), (0, 4, .2)]),
+    ([(0, 0, .3), (0, 1, .3), (0, 2, .5)], [(0, 0, .3), (0, 1, .3), (0, 2, .5)]),
+    ([(0, 0, .5), (0, 1, .2), (1, 0, .1), (1, 1, .3)], [(0, 1, .2), (1, 0, .1), (1, 1, .3)]),
+    ([(0, 0, .5), (1, 1, .6), (0, 1, .1)], [(0, 1, .1), (0, 1, .1)]),
+]
+
+
+def _m(rows):
+    return np.array(rows, dtype=_abi.MATCH_DTYPE) if len(rows) else np.zeros(0, _abi.MATCH_DTYPE)
+
+
+@pytest.mark.parametrize("inp,exp", RESOLVE_KAT)
+def test_gpu_resolve_known_answers(ctx, inp, exp):
+    assert ctx.resolve_match_list(_m(inp)).tobytes() == _m(exp).tobytes()
+    assert ctx.last_kernel == "resolve_next_smaller_kernel"
+
+
+def test_gpu_resolve_random_vs_oracle_and_reference(ctx, oracle):
+    rng = np.random.default_rng(432)
+    ref_ok = oracle.ref() is not None
+    assert len(ctx.resolve_match_list(_m([]))) == 0
+    for t in range(120):
+        n = int(rng.integers(1, 400))
+        k = int(rng.integers(1, 12))
+        m = np.zeros(n, _abi.MATCH_DTYPE)
+        m["LeftIndex"], m["RightIndex"] = rng.integers(0, k, n), rng.integers(0, k, n)
+        m["MatchValue"] = rng.integers(0, 10, n) / 8.0  # many ties: the strict '>' of :451 matters
+        if t % 5 == 0:
+            m["MatchValue"][rng.integers(0, n, 1 + n // 6)] = np.nan
+        if t % 7 == 0:
+            m["MatchValue"][rng.integers(0, n, 1 + n // 6)] = np.inf
+        got = ctx.resolve_match_list(m)
+        assert got.tobytes() == oracle.resolve_match_list(m).tobytes(), t
+        if ref_ok:
+            assert got.tobytes() == oracle.ref_resolve_match_list(m).tobytes(), t
+
+
+def test_gpu_resolve_long_lists(ctx, oracle):
+    """One giant group (the sequential worst case of the per-group stack pass) and the dense winners of a real
+    frame pair (distinct LeftIndex, conflicts through RightIndex only, NO_MATCH records skipped)."""
+    rng = np.random.default_rng(7)
+    n = 20000
+    m = np.zeros(n, _abi.MATCH_DTYPE)
+    m["LeftIndex"], m["RightIndex"] = 3, rng.integers(0, 50, n)
+    m["MatchValue"] = rng.random(n)
+    assert ctx.resolve_match_list(m).tobytes() == oracle.resolve_match_list(m).tobytes()
+    left, right = synth.make_pairs(1, 160, 40, 1, shift=9, noise_sigma=2.0, seed=11)
+    p = _abi.make_params(tmpl_w=8, tmpl_h=8, cost="sad", search_min=2, search_max=30, accept_threshold=0.05)
+    win = ctx.match_dense(left, right, p, mask=_abi.OUT_MATCHES)["matches"][0]
+    kept = win[win["RightIndex"] != _abi.NO_MATCH]
+    assert 0 < len(kept) < len(win)
+    exp = oracle.resolve_match_list(kept)
+    assert ctx.resolve_match_list(win, skip_unmatched=True).tobytes() == exp.tobytes()
+    assert ctx.resolve_match_list(kept).tobytes() == exp.tobytes()
+    assert len(exp) <= len(kept)

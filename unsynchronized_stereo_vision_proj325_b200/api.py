@@ -23,6 +23,7 @@ EXPORTS = (
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
     "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_wait",
     "usv_stream_bytes_per_pair", "usv_probe_issue_rate", "usv_match_contours",
+    "usv_resolve_match_list", "usv_resolve_match_list_device",
 )
 
 
@@ -229,6 +230,16 @@ class Context:
                                       C.c_double(accept_threshold), _ptr(out), C.c_int64(len(out)), C.byref(n), _ptr(cm))
         self._check(rc, "usv_match_contours")
         return out[:n.value], cm[:nl, :nr]
+
+    def resolve_match_list(self, matches, skip_unmatched=False):
+        """ResolveMatchList (P/Main.cpp:432-477) on the GPU: MATCH_DTYPE array -> the reference's TentativeMatch."""
+        m = np.ascontiguousarray(matches, dtype=_abi.MATCH_DTYPE)
+        out = np.zeros(max(len(m), 1), dtype=_abi.MATCH_DTYPE)
+        n = C.c_int64()
+        rc = lib().usv_resolve_match_list(self._h, _ptr(m), C.c_int64(len(m)), C.c_int32(int(skip_unmatched)), _ptr(out),
+                                          C.c_int64(len(out)), C.byref(n))
+        self._check(rc, "usv_resolve_match_list")
+        return out[:n.value]
 
     def probe_issue_rate(self, which=0, target_ms=20.0):
         """Sustained thread-instructions/s of VABSDIFF4.U8.ACC (0) / IDP.4A (1): the ALU roofline denominator."""

@@ -1,6 +1,6 @@
 // SearchAlgorithms.cpp — host side of the block-search drop-in. Every cost is computed by the
 // sm_100a kernels behind the C-ABI; this file only marshals vectors, applies the accept test to
-// dumped candidate costs (template overload) and restates ResolveMatchList.
+// dumped candidate costs (template overload) and forwards ResolveMatchList to the GPU resolve.
 #include "../../../include/SearchAlgorithms.hpp"
 
 #include <cmath>
@@ -125,23 +125,22 @@ void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView
   }
 }
 
-// P/Main.cpp:432-477. The outer while(AnyConflict) of the reference runs its body once (Matcher is
-// cleared at :475 and MatchCounter is never reset), DeassignedMatch is write-only: what remains is
-// this single greedy pass.
+// P/Main.cpp:432-477 behind the original signature. The greedy pass runs on the GPU (usv_resolve.cu: it factors
+// into next-strictly-smaller chains per LeftIndex / RightIndex group, so lists of any length resolve in
+// O(M log M)); the output is the reference's TentativeMatch entry for entry, duplicates included.
 void ResolveMatchList(std::vector<Match> Matcher, std::vector<Match>& TentativeMatch) {
-  TentativeMatch.clear();
-  for (size_t k = 0; k < Matcher.size(); ++k) {
-    bool Conflict = false;
-    for (size_t i = 0; i < TentativeMatch.size(); ++i) {
-      if (TentativeMatch[i].LeftIndex == Matcher[k].LeftIndex || TentativeMatch[i].RightIndex == Matcher[k].RightIndex) {  // :450
-        if (TentativeMatch[i].MatchValue > Matcher[k].MatchValue) {  // :451 — strictly worse only
-          TentativeMatch[i] = Matcher[k];
-          Conflict = true;
-        }
-      }
-    }
-    if (!Conflict) TentativeMatch.push_back(Matcher[k]);  // :463-466, :469
-  }
+  TentativeMatch.clear();  // :437
+  if (Matcher.empty()) return;  // :441
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  usv_ctx* ctx = tc.get(0);
+  if (!ctx) return;
+  static_assert(sizeof(Match) == sizeof(usv_match), "Match must stay bit-identical to usv_match");
+  std::vector<usv_match> out(Matcher.size());
+  int64_t n = 0;
+  const int rc = usv_resolve_match_list(ctx, reinterpret_cast<const usv_match*>(Matcher.data()), (int64_t)Matcher.size(), 0, out.data(),
+                                        (int64_t)out.size(), &n);
+  if (!tc.check(ctx, rc, "usv_resolve_match_list")) return;
+  for (int64_t k = 0; k < n; ++k) TentativeMatch.push_back({out[k].LeftIndex, out[k].RightIndex, out[k].MatchValue});
 }
 
 // P/Main.cpp:483-499 (a tiny O(n*m) host join; its output feeds MovingObjectDistanceCalculator's index triples)

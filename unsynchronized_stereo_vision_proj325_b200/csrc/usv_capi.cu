@@ -19,6 +19,9 @@ cudaError_t launch_direct(const DevJob& J, int n_pairs, cudaStream_t st);
 cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches);
 cudaError_t launch_contour_descriptors(const int* pts, const int* off, int n, double* desc, cudaStream_t st);
 cudaError_t launch_contour_costs(const double* dl, int nl, const double* dr, int nr, double* cost, cudaStream_t st);
+size_t resolve_workspace_bytes(long long n);
+cudaError_t launch_resolve(const usv_match* d_in, long long n, int skip_unmatched, usv_match* d_out, long long cap, long long* d_n_out,
+                           void* d_ws, size_t ws_bytes, cudaStream_t st, int* n_launches);
 cudaError_t run_issue_probe(int which, int sms, double target_ms, double* lane_inst_per_s, uint32_t* d_scratch, cudaStream_t st);
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
 cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
@@ -46,7 +49,7 @@ struct usv_ctx {
   double* lut[3] = {nullptr, nullptr, nullptr};
   int lut_n[3] = {0, 0, 0};
   // grow-only scratch for the host paths
-  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8];
+  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws;
 };
 
 static const int kNumOut = 8;
@@ -191,6 +194,7 @@ extern "C" int usv_destroy(usv_ctx* ctx) {
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   for (auto& b : ctx->out) if (b.p) cudaFree(b.p);
   for (auto& b : ctx->misc) if (b.p) cudaFree(b.p);
+  if (ctx->resolve_ws.p) cudaFree(ctx->resolve_ws.p);
   for (double* l : ctx->lut) if (l) cudaFree(l);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -387,6 +391,53 @@ static int up(usv_ctx* ctx, DevBuf& b, const void* h, size_t bytes) {
   int rc = grow(ctx, b, bytes ? bytes : 16);
   if (rc) return rc;
   if (bytes) CU(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return USV_OK;
+}
+
+// ---- ResolveMatchList on the GPU (usv_resolve.cu) ------------------------------------------
+static int resolve_device(usv_ctx* ctx, const usv_match* d_in, int64_t n, int32_t skip_unmatched, usv_match* d_out, int64_t cap,
+                          int64_t* d_n_out, cudaStream_t st) {
+  if (n < 0 || cap < 0 || n >= 0x7fffffffll) return fail(ctx, USV_ERR_INVALID_ARG, "match list length %lld out of range", (long long)n);
+  if (!d_n_out || (n > 0 && (!d_in || (cap > 0 && !d_out)))) return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
+  CU(cudaSetDevice(ctx->device));
+  const size_t ws = n ? usv::resolve_workspace_bytes(n) : 0;
+  int rc = grow(ctx, ctx->resolve_ws, ws ? ws : 16);
+  if (rc) return rc;
+  int nl = 0;
+  cudaError_t e = usv::launch_resolve(d_in, n, skip_unmatched, d_out, cap, (long long*)d_n_out, ctx->resolve_ws.p, ws, st, &nl);
+  if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "resolve launch: %s", cudaGetErrorString(e));
+  ctx->launches += nl;
+  if (nl) ctx->last_kernel = "resolve_next_smaller_kernel";
+  return USV_OK;
+}
+
+extern "C" int usv_resolve_match_list_device(usv_ctx* ctx, const usv_match* d_in, int64_t n, int32_t skip_unmatched, usv_match* d_out,
+                                             int64_t cap, int64_t* d_n_out, void* cuda_stream) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  return resolve_device(ctx, d_in, n, skip_unmatched, d_out, cap, d_n_out, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int usv_resolve_match_list(usv_ctx* ctx, const usv_match* h_in, int64_t n, int32_t skip_unmatched, usv_match* h_out,
+                                      int64_t cap, int64_t* n_out) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n < 0 || cap < 0 || !n_out || (n > 0 && !h_in) || (cap > 0 && !h_out)) return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  *n_out = 0;
+  if (n == 0) return USV_OK;
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  const int64_t room = cap < n ? cap : n;  // the output is never longer than the input
+  if ((rc = up(ctx, ctx->misc[0], h_in, sizeof(usv_match) * (size_t)n))) return rc;
+  if ((rc = grow(ctx, ctx->misc[1], sizeof(usv_match) * (size_t)(room ? room : 1)))) return rc;
+  if ((rc = grow(ctx, ctx->misc[2], sizeof(int64_t)))) return rc;
+  if ((rc = resolve_device(ctx, (const usv_match*)ctx->misc[0].p, n, skip_unmatched, (usv_match*)ctx->misc[1].p, room,
+                           (int64_t*)ctx->misc[2].p, ctx->stream)))
+    return rc;
+  int64_t total = 0;
+  CU(cudaMemcpyAsync(&total, ctx->misc[2].p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int64_t m = total < room ? total : room;
+  if (m > 0) CU(cudaMemcpy(h_out, ctx->misc[1].p, sizeof(usv_match) * (size_t)m, cudaMemcpyDeviceToHost));
+  *n_out = total;
   return USV_OK;
 }
 
