@@ -179,6 +179,14 @@ class Context:
                                           C.byref(params), C.byref(d_out), C.c_void_p(int(stream)))
         self._check(rc, "usv_match_dense_device")
 
+    def match_templates_device(self, d_left, d_right, frame, n_pairs, d_tx, d_ty, n_templates, params, d_out, stream=0,
+                               d_cost_rows=None, d_score_rows=None, row_cap=0):
+        """Raw device pointers (ints), explicit template list; asynchronous on `stream`."""
+        rc = lib().usv_match_templates_device(self._h, _ptr(d_left), _ptr(d_right), C.byref(frame), C.c_int32(n_pairs), _ptr(d_tx),
+                                              _ptr(d_ty), C.c_int32(n_templates), C.byref(params), C.byref(d_out), _ptr(d_cost_rows),
+                                              _ptr(d_score_rows), C.c_int32(row_cap), C.c_void_p(int(stream)))
+        self._check(rc, "usv_match_templates_device")
+
     # ---- distance family --------------------------------------------------------
     def disparity_to_distance(self, disp, kind):
         d = np.ascontiguousarray(disp, np.int32)
