@@ -42,6 +42,7 @@ constexpr int kRB = 4;          // rows per staging block
 constexpr int kLW = 32;         // words per L copy row (128 B)
 constexpr int kRW = 44;         // words per R copy row (40 used; 44 keeps the four copies on disjoint banks)
 constexpr int kRowWords = 4 * kLW + 4 * kRW;  // one ring row: 4 L copies + 4 R copies
+constexpr int kRingWords = 4 * kRB * kRowWords;  // entering + leaving halves, each double-buffered by block
 constexpr int kCodeOff = 32;    // candidate code = x0 -/+ d + kCodeOff: a valid candidate of column i has x0 -/+ d >= -4i >= -28
 
 struct DenseCfg {
@@ -49,8 +50,8 @@ struct DenseCfg {
   int n_xtiles;
   int bh;           // output rows per band
   int n_bands;
-  int nr;           // ring rows (>= th + 2*kRB)
   int xb;           // bits of the candidate code inside the key
+  int ring_words;   // shared-memory words of the row ring
   int x_off;        // tile t starts at x = t * stride_px - x_off (multiple of 4)
 };
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // i0-1, i0-1-NW, ... and i1+NW-1, i1+2NW-1, ... start at BIG = 2^(31-xb) instead of 0. Every invalid
 // window then contains exactly one BIG column and its key carries bit 31 (true keys stay below 2^31,
 // checked on the host), every valid window contains none. No per-element masks, no second code path.
-template <int DIR, int NW, bool FOLD>
+template <int DIR, int NW, bool FOLD, bool RING2>
 __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
                                            const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
                                            const int XR0, const int run, const int dbase, const int r_shift,
@@ -82,7 +83,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const int ul = run, dl = lane >> 2, q = dl & 3, jh = dl >> 2;
   const int x0 = X0 + p + 32 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i, i < 8)
   const bool guest = FOLD && (lane & 3) == 0;
-  const int th = J.th, nr = cfg.nr;
+  const int th = J.th;
   const int row_words = J.row_stride >> 2;
   const uint32_t key_scale = 1u << cfg.xb;
   const uint32_t minus_scale = key_scale * minus_one;  // -(1 << xb), kept opaque so the multiply stays an IMAD
@@ -110,37 +111,61 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
     }
   }
 
-  // ---- staging: a block of kRB rows is 18 chunks of 4 words per row (8 of the L segment, 10 of the R
-  // segment); thread t < 18 * kRB takes chunk t % 18 of row t / 18: five aligned global words -> 12 funnel
-  // shifts -> the four byte-shifted copies, one STS.128 each
+  // ---- staging. Two ring layouts:
+  //   RING2 = false (th <= 16): one ring of th + 2*kRB rows; a row is fetched once and read twice, when it enters
+  //           the windows and th rows later when it leaves them.
+  //   RING2 = true  (taller templates): the ring depth no longer grows with th — 2*kRB slots for the entering rows
+  //           and 2*kRB for the leaving rows, each double-buffered by block of kRB rows (row r sits in slot r & 7 of
+  //           its half); a row is fetched twice, th rows apart (the second fetch is an L2 hit), which leaves shared
+  //           memory for tall bands (32x32 templates: 73-row bands instead of 14).
+  // A block is 18 chunks of 4 words per row (8 of the L segment, 10 of the R segment), per half: thread t takes
+  // task t (RING2: threads 0..15 also task 128 + t). A task turns five aligned global words into the four
+  // byte-shifted copies of its chunk: 12 funnel shifts, one STS.128 per copy.
   constexpr int kChunks = kLW / 4 + 10;
-  const bool stager = tid < kChunks * kRB;
-  const int st_row = tid / kChunks, st_c = tid - st_row * kChunks;
-  const bool st_left = st_c < kLW / 4;
-  const int st_w = st_left ? 4 * st_c : 4 * (st_c - kLW / 4);
-  const int st_kw = st_left ? kLW : kRW;
-  const int st_off = (st_left ? 0 : 4 * kLW) + st_w;
-  const uint32_t* st_g = (st_left ? Lg : Rg) + (long long)st_row * row_words;
-  int gi[5];
+  struct StageTask {
+    const uint32_t* g;  // frame rows of the band (L or R)
+    int row, back;      // row inside the block; th for the leaving half, 0 for the entering half
+    int gb;             // first global word of the chunk (before clamping to the frame row)
+    int off, kw;        // word offset inside the ring (half + copy 0 + chunk), words between copies
+    bool on;
+  };
+  auto make_task = [&](int k) {
+    StageTask t;
+    t.on = k < (RING2 ? 2 : 1) * kRB * kChunks;
+    const int half = k >= kRB * kChunks ? 1 : 0, rem = k - half * kRB * kChunks;
+    t.row = rem / kChunks;
+    const int c = rem - t.row * kChunks;
+    const bool left = c < kLW / 4;
+    const int w = left ? 4 * c : 4 * (c - kLW / 4);
+    t.g = left ? Lg : Rg;
+    t.back = half ? th : 0;
+    t.gb = ((left ? X0 : XR0) >> 2) + w;  // X0, XR0 are multiples of 4
+    t.kw = left ? kLW : kRW;
+    t.off = half * 2 * kRB * kRowWords + (left ? 0 : 4 * kLW) + w;
+    return t;
+  };
+  const StageTask task_a = make_task(tid), task_b = make_task(kDenseThreads + tid);
+  const int nr = th + 2 * kRB;  // !RING2: ring depth
+  int stage_slot = task_a.row;  // !RING2: ring slot of this thread's row in the next block to stage
+  auto run_task = [&](const StageTask& t, int row_begin) {
+    const int r = row_begin + t.row, gr = r - t.back;
+    if (!t.on || r >= rows_in || gr < 0) return;
+    const uint32_t* gp = t.g + (long long)gr * row_words;
+    uint32_t w[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) gi[k] = min(max(((st_left ? X0 : XR0) >> 2) + st_w + k, 0), row_words - 1);  // X0, XR0 are multiples of 4
-  int stage_slot = st_row;  // ring slot of this thread's row in the next block to stage
+    for (int k = 0; k < 5; ++k) w[k] = __ldg(gp + min(max(t.gb + k, 0), row_words - 1));
+    uint32_t* dst = s_ring + (size_t)(RING2 ? (r & (2 * kRB - 1)) : stage_slot) * kRowWords + t.off;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int c = 1; c < 4; ++c)
+      *reinterpret_cast<uint4*>(dst + c * t.kw) =
+          make_uint4(__funnelshift_r(w[0], w[1], 8 * c), __funnelshift_r(w[1], w[2], 8 * c),
+                     __funnelshift_r(w[2], w[3], 8 * c), __funnelshift_r(w[3], w[4], 8 * c));
+  };
   auto stage = [&](int row_begin) {
-    if (stager && row_begin + st_row < rows_in) {
-      const uint32_t* gp = st_g + (long long)row_begin * row_words;
-      uint32_t w[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) w[k] = __ldg(gp + gi[k]);
-      uint32_t* dst = s_ring + (size_t)stage_slot * kRowWords + st_off;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-#pragma unroll
-      for (int c = 1; c < 4; ++c)
-        *reinterpret_cast<uint4*>(dst + c * st_kw) =
-            make_uint4(__funnelshift_r(w[0], w[1], 8 * c), __funnelshift_r(w[1], w[2], 8 * c),
-                       __funnelshift_r(w[2], w[3], 8 * c), __funnelshift_r(w[3], w[4], 8 * c));
-    }
-    stage_slot += kRB;
-    if (stage_slot >= nr) stage_slot -= nr;
+    run_task(task_a, row_begin);
+    if (RING2) run_task(task_b, row_begin);
+    else { stage_slot += kRB; if (stage_slot >= nr) stage_slot -= nr; }
   };
 
   // this thread's operand words inside a ring row: L words [8ul, 8ul+8) of copy p; R words
@@ -152,7 +177,9 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const bool b4 = (dl >> 2) & 1, b3 = (dl >> 1) & 1, b2 = dl & 1;
   uint32_t* my_best = s_best + p * 32 + 8 * ul + own_i;
 
-  int slot_new = 0, slot_old = 0;
+  const uint32_t* my_lo = my_l + (RING2 ? 2 * kRB * kRowWords : 0);  // RING2: the half that holds the leaving rows
+  const uint32_t* my_ro = my_r + (RING2 ? 2 * kRB * kRowWords : 0);
+  int slot_new = 0, slot_old = 0;  // !RING2
 
   // one row of the band: the row enters the windows (V += h), the row th above leaves them (V -= h), the
   // window sums become keys and are folded into the running best. The three phases of a pass (warm-up,
@@ -161,10 +188,11 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   auto row_body = [&](auto has_old_t, auto has_keys_t, int row) {
     constexpr bool HAS_OLD = decltype(has_old_t)::value, HAS_KEYS = decltype(has_keys_t)::value;
     {
-      const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot_new * kRowWords);
-      const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot_new * kRowWords);
+      const int slot = RING2 ? (row & (2 * kRB - 1)) : slot_new;
+      if (!RING2) slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
+      const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot * kRowWords);
+      const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot * kRowWords);
       const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
-      slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
       const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
       const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
@@ -173,10 +201,11 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
         for (int j = 0; j < 4; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
     }
     if (HAS_OLD) {
-      const uint4* lo = reinterpret_cast<const uint4*>(my_l + (size_t)slot_old * kRowWords);
-      const uint4* ro = reinterpret_cast<const uint4*>(my_r + (size_t)slot_old * kRowWords);
+      const int slot = RING2 ? (row & (2 * kRB - 1)) : slot_old;
+      if (!RING2) slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
+      const uint4* lo = reinterpret_cast<const uint4*>(my_lo + (size_t)slot * kRowWords);
+      const uint4* ro = reinterpret_cast<const uint4*>(my_ro + (size_t)slot * kRowWords);
       const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
-      slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
       const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
       const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
@@ -243,8 +272,8 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
       }
     }
   };
-  // every kRB rows: all warps are done with the previous block (its oldest ring rows may be overwritten), the
-  // block staged meanwhile becomes visible, and the block after it is fetched
+  // every kRB rows: all warps are done with the previous block (its ring slots may be overwritten), the block
+  // staged meanwhile becomes visible, and the block after it is fetched
   auto block_edge = [&](int row) {
     if ((row & (kRB - 1)) == 0) {
       __syncthreads();
@@ -273,12 +302,12 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
 // NW = tw / 4 packed words per window (2..8: the halo columns come from one neighbouring lane).
-template <int DIR, int NW>
+template <int DIR, int NW, bool RING2>
 __global__ void __launch_bounds__(kDenseThreads, 4)
 dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
-  uint32_t* s_ring = smem_u32;                                  // [nr][kRowWords]
-  uint32_t* s_best = smem_u32 + (size_t)cfg.nr * kRowWords;     // [bh][4][32]
+  uint32_t* s_ring = smem_u32;                                  // RING2 ? [2][2*kRB][kRowWords] : [th + 2*kRB][kRowWords]
+  uint32_t* s_best = smem_u32 + cfg.ring_words;                 // [bh][4][32]
 
   const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;   // p: byte phase of this warp
   const int ul = lane & 3, dl = lane >> 2;
@@ -331,8 +360,8 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
     const int r_shift = DIR < 0 ? -((D0_mine - D0) >> 2) : ((D0_mine - D0) >> 2);
-    if (fold_pass) dense_pass<DIR, NW, true>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
-    else dense_pass<DIR, NW, false>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    if (fold_pass) dense_pass<DIR, NW, true, RING2>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    else dense_pass<DIR, NW, false, RING2>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
   }
   __syncthreads();
 
@@ -381,20 +410,21 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   cfg.xb = ceil_log2((long long)J.nxc + kCodeOff + 1);
   const long long smax = 255ll * J.n_elems;
   if (ceil_log2(smax + 1) + cfg.xb > 31) return cudaErrorNotSupported;  // bit 31 marks invalid candidates
-  cfg.nr = J.th + 2 * kRB;
   // bands: as tall as shared memory allows (amortises the th-1 warm-up rows), but enough CTAs to fill 148 SMs
   const int smem_budget = 56 * 1024;  // 4 CTAs / SM
-  int bh_max = (smem_budget - cfg.nr * kRowWords * 4) / 512;
+  const bool ring2 = J.th > 16;  // measured: the short double-fetched ring pays from 24-row templates on
+  cfg.ring_words = ring2 ? kRingWords : (J.th + 2 * kRB) * kRowWords;
+  int bh_max = (smem_budget - cfg.ring_words * 4) / 512;
   if (bh_max < 8) return cudaErrorNotSupported;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
   while ((long long)n_bands * cfg.n_xtiles * n_pairs < 148 * 3 && n_bands < (J.nyc + 15) / 16) ++n_bands;
   cfg.bh = (J.nyc + n_bands - 1) / n_bands;
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
-  const size_t smem = (size_t)cfg.nr * kRowWords * 4 + (size_t)cfg.bh * 512;
+  const size_t smem = (size_t)cfg.ring_words * 4 + (size_t)cfg.bh * 512;
   dim3 grid(cfg.n_xtiles, cfg.n_bands, n_pairs), block(kDenseThreads);
 #define USV_DENSE_LAUNCH(D, NWW)                                                                          \
   {                                                                                                       \
-    auto kfn = dense_sad_argmin_kernel<D, NWW>;                                                           \
+    auto kfn = ring2 ? dense_sad_argmin_kernel<D, NWW, true> : dense_sad_argmin_kernel<D, NWW, false>;                                                         \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     if (e != cudaSuccess) return e;                                                                       \
     kfn<<<grid, block, smem, st>>>(J, cfg, 0xffffffffu);                                                  \
