@@ -197,6 +197,14 @@ int usv_resolve_match_list_device(usv_ctx *ctx, const usv_match *d_in, int64_t n
                                   int32_t skip_unmatched, usv_match *d_out,
                                   int64_t cap, int64_t *d_n_out, void *cuda_stream);
 
+/* IDMatcher, P/Main.cpp:483-499: joins the current inter-frame matches with the previous ones on
+ * cur.RightIndex == old.LeftIndex, i-major / j-minor. out3: (x, y, z) int32 triples; as in the reference
+ * (comma operator at :492) every triple is (old.RightIndex, 0, 0). *n_out = full count even beyond cap.
+ * Host pointers. */
+int usv_id_matcher(usv_ctx *ctx, const usv_match *h_cur, int64_t n_cur,
+                   const usv_match *h_old, int64_t n_old, int32_t *h_out3,
+                   int64_t cap, int64_t *n_out);
+
 /* ---- distance family (host buffers; one tiny kernel each) ---------------- */
 int usv_disparity_to_distance(usv_ctx *ctx, const int32_t *h_disp, int64_t n,
                               int32_t distance_kind, double *h_dist);

@@ -310,3 +310,50 @@ def test_gpu_resolve_long_lists(ctx, oracle):
     assert ctx.resolve_match_list(win, skip_unmatched=True).tobytes() == exp.tobytes()
     assert ctx.resolve_match_list(kept).tobytes() == exp.tobytes()
     assert len(exp) <= len(kept)
+
+
+def test_gpu_id_matcher_vs_oracle_and_reference(ctx, oracle):
+    """IDMatcher (P/Main.cpp:483-499) on the GPU, comma-operator quirk of :492 included."""
+    cur = _m([(0, 5, .1), (1, 7, .2), (2, 5, .3)])
+    old = _m([(5, 9, .1), (7, 3, .2), (8, 1, .3)])
+    assert ctx.id_matcher(cur, old).tolist() == [[9, 0, 0], [3, 0, 0], [9, 0, 0]]
+    assert len(ctx.id_matcher(cur, _m([]))) == 0 and len(ctx.id_matcher(_m([]), old)) == 0
+    rng = np.random.default_rng(483)
+    ref_ok = oracle.ref() is not None
+    for _ in range(40):
+        a, b = np.zeros(int(rng.integers(1, 300)), _abi.MATCH_DTYPE), np.zeros(int(rng.integers(1, 300)), _abi.MATCH_DTYPE)
+        for m in (a, b):
+            m["LeftIndex"], m["RightIndex"] = rng.integers(0, 20, len(m)), rng.integers(0, 20, len(m))
+        got = ctx.id_matcher(a, b).tolist()
+        assert got == oracle.id_matcher(a, b).tolist()
+        if ref_ok:
+            assert got == oracle.ref_id_matcher(a, b).tolist()
+
+
+def test_unsynchronised_extrapolation(ctx, oracle):
+    """an object that moves between the other camera's frames is ranged at THIS camera's capture time
+    by tracking it through three frames and extrapolating (P/DistanceCalculator.cpp:53-84). Constant pixel velocity:
+    the shift grows by 3 px per 33 ms frame; this camera fires 22 ms after the other camera's newest frame."""
+    from unsynchronized_stereo_vision_proj325_b200 import pipeline
+    shifts, t_other, t_this = (31, 34, 37), (0.000, 0.033, 0.066), 0.088
+    frames = [synth.make_pairs(1, 320, 64, 1, shift=s, noise_sigma=0.0, seed=9) for s in shifts]
+    left = frames[0][0][0]
+    assert all(np.array_equal(f[0][0], left) for f in frames)  # same seed: one left frame, three right frames
+    others = [f[1][0] for f in frames]
+    tpl = np.array([[100, 10], [150, 20], [200, 30], [260, 40]], np.int32)
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad", search_max=60, distance_kind=_abi.DIST_POWERLAW)
+    res = pipeline.extrapolated_distances(ctx, _abi.LEFT_CAM, left, t_this, others, t_other, tpl, p)
+    assert res["accepted"].all()
+    assert np.array_equal(res["tracks"], np.array([tpl[:, 0] - s for s in shifts], np.float32))
+    # constant velocity 3 px / 33 ms -> at t_this the other camera would see the object 2 px further: disparity 39
+    exp_now = oracle.distance([39], _abi.DIST_POWERLAW)[0]
+    assert np.allclose(res["distance"], exp_now, rtol=1e-12)
+    assert np.allclose(res["nearest_distance"], oracle.distance([37], _abi.DIST_POWERLAW)[0], rtol=1e-12)
+    # and bit for bit what the restated reference function gives on the same centre points
+    half = 8.0
+    cen = lambda xs: np.stack([xs + half, tpl[:, 1] + half], 1).astype(np.float32)  # noqa: E731
+    ns = lambda t: int(round(t * 1e9))  # noqa: E731
+    exp = oracle.moving_object_distance(_abi.LEFT_CAM, ns(t_this), cen(tpl[:, 0].astype(np.float32)), cen(res["tracks"][2]),
+                                        cen(res["tracks"][1]), cen(res["tracks"][0]), np.repeat(np.arange(4)[:, None], 3, 1),
+                                        ns(t_other[2]), ns(t_other[1]), ns(t_other[0]))
+    assert np.allclose(res["distance"], exp, rtol=1e-12)

@@ -23,7 +23,7 @@ EXPORTS = (
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
     "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_wait",
     "usv_stream_bytes_per_pair", "usv_probe_issue_rate", "usv_match_contours",
-    "usv_resolve_match_list", "usv_resolve_match_list_device",
+    "usv_resolve_match_list", "usv_resolve_match_list_device", "usv_id_matcher",
 )
 
 
@@ -247,6 +247,18 @@ class Context:
         rc = lib().usv_resolve_match_list(self._h, _ptr(m), C.c_int64(len(m)), C.c_int32(int(skip_unmatched)), _ptr(out),
                                           C.c_int64(len(out)), C.byref(n))
         self._check(rc, "usv_resolve_match_list")
+        return out[:n.value]
+
+    def id_matcher(self, cur, old):
+        """IDMatcher (P/Main.cpp:483-499) on the GPU: two MATCH_DTYPE lists -> [n, 3] int32 triples."""
+        a = np.ascontiguousarray(cur, dtype=_abi.MATCH_DTYPE)
+        b = np.ascontiguousarray(old, dtype=_abi.MATCH_DTYPE)
+        n = C.c_int64()
+        rc = lib().usv_id_matcher(self._h, _ptr(a), C.c_int64(len(a)), _ptr(b), C.c_int64(len(b)), None, C.c_int64(0), C.byref(n))
+        self._check(rc, "usv_id_matcher")
+        out = np.zeros((max(n.value, 1), 3), np.int32)
+        rc = lib().usv_id_matcher(self._h, _ptr(a), C.c_int64(len(a)), _ptr(b), C.c_int64(len(b)), _ptr(out), C.c_int64(len(out)), C.byref(n))
+        self._check(rc, "usv_id_matcher")
         return out[:n.value]
 
     def probe_issue_rate(self, which=0, target_ms=20.0):

@@ -143,15 +143,27 @@ void ResolveMatchList(std::vector<Match> Matcher, std::vector<Match>& TentativeM
   for (int64_t k = 0; k < n; ++k) TentativeMatch.push_back({out[k].LeftIndex, out[k].RightIndex, out[k].MatchValue});
 }
 
-// P/Main.cpp:483-499 (a tiny O(n*m) host join; its output feeds MovingObjectDistanceCalculator's index triples)
+// P/Main.cpp:483-499 behind the original signature; the join runs on the GPU (usv_resolve.cu). Its output feeds
+// MovingObjectDistanceCalculator's index triples; the comma-operator quirk of :492 is kept: (old.RightIndex, 0, 0).
 void IDMatcher(std::vector<Match> InterframeMatchIndexes, std::vector<Match> OldInterframeMatchIndexes,
                std::vector<cv::Point3i>& InterframeMatchIndexesComplete) {
   InterframeMatchIndexesComplete.clear();  // :486
-  for (size_t i = 0; i < InterframeMatchIndexes.size(); ++i)
-    for (size_t j = 0; j < OldInterframeMatchIndexes.size(); ++j)
-      if (InterframeMatchIndexes[i].RightIndex == OldInterframeMatchIndexes[j].LeftIndex)  // :491
-        // :492 `(Point3i)(cur, old.RightIndex)`: the comma operator keeps only old.RightIndex -> (old.RightIndex, 0, 0)
-        InterframeMatchIndexesComplete.push_back(cv::Point3i((int)OldInterframeMatchIndexes[j].RightIndex, 0, 0));
+  if (InterframeMatchIndexes.empty() || OldInterframeMatchIndexes.empty()) return;
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  usv_ctx* ctx = tc.get(0);
+  if (!ctx) return;
+  const usv_match* cur = reinterpret_cast<const usv_match*>(InterframeMatchIndexes.data());
+  const usv_match* old = reinterpret_cast<const usv_match*>(OldInterframeMatchIndexes.data());
+  const int64_t n_cur = (int64_t)InterframeMatchIndexes.size(), n_old = (int64_t)OldInterframeMatchIndexes.size();
+  std::vector<int32_t> out(3 * 64);
+  int64_t n = 0;
+  int rc = usv_id_matcher(ctx, cur, n_cur, old, n_old, out.data(), (int64_t)out.size() / 3, &n);
+  if (rc == USV_OK && n > (int64_t)out.size() / 3) {
+    out.resize(3 * (size_t)n);
+    rc = usv_id_matcher(ctx, cur, n_cur, old, n_old, out.data(), n, &n);
+  }
+  if (!tc.check(ctx, rc, "usv_id_matcher")) return;
+  for (int64_t k = 0; k < n; ++k) InterframeMatchIndexesComplete.push_back(cv::Point3i(out[3 * k], out[3 * k + 1], out[3 * k + 2]));
 }
 
 int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,

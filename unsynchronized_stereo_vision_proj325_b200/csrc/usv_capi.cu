@@ -22,6 +22,9 @@ cudaError_t launch_contour_costs(const double* dl, int nl, const double* dr, int
 size_t resolve_workspace_bytes(long long n);
 cudaError_t launch_resolve(const usv_match* d_in, long long n, int skip_unmatched, usv_match* d_out, long long cap, long long* d_n_out,
                            void* d_ws, size_t ws_bytes, cudaStream_t st, int* n_launches);
+size_t id_matcher_workspace_bytes(long long n_cur);
+cudaError_t launch_id_matcher(const usv_match* d_cur, long long n_cur, const usv_match* d_old, long long n_old, int* d_out3,
+                              long long cap, long long* d_n_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t run_issue_probe(int which, int sms, double target_ms, double* lane_inst_per_s, uint32_t* d_scratch, cudaStream_t st);
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
 cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
@@ -437,6 +440,36 @@ extern "C" int usv_resolve_match_list(usv_ctx* ctx, const usv_match* h_in, int64
   CU(cudaStreamSynchronize(ctx->stream));
   const int64_t m = total < room ? total : room;
   if (m > 0) CU(cudaMemcpy(h_out, ctx->misc[1].p, sizeof(usv_match) * (size_t)m, cudaMemcpyDeviceToHost));
+  *n_out = total;
+  return USV_OK;
+}
+
+extern "C" int usv_id_matcher(usv_ctx* ctx, const usv_match* h_cur, int64_t n_cur, const usv_match* h_old, int64_t n_old,
+                              int32_t* h_out3, int64_t cap, int64_t* n_out) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n_cur < 0 || n_old < 0 || cap < 0 || !n_out || (n_cur > 0 && !h_cur) || (n_old > 0 && !h_old) || (cap > 0 && !h_out3) ||
+      n_cur >= 0x7fffffffll || n_old >= 0x7fffffffll)
+    return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  *n_out = 0;
+  if (n_cur == 0 || n_old == 0) return USV_OK;  // P/Main.cpp:487-489
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = up(ctx, ctx->misc[0], h_cur, sizeof(usv_match) * (size_t)n_cur))) return rc;
+  if ((rc = up(ctx, ctx->misc[1], h_old, sizeof(usv_match) * (size_t)n_old))) return rc;
+  if ((rc = grow(ctx, ctx->misc[2], sizeof(int32_t) * 3 * (size_t)(cap ? cap : 1)))) return rc;
+  if ((rc = grow(ctx, ctx->misc[3], sizeof(int64_t)))) return rc;
+  const size_t ws = usv::id_matcher_workspace_bytes(n_cur);
+  if ((rc = grow(ctx, ctx->resolve_ws, ws))) return rc;
+  cudaError_t e = usv::launch_id_matcher((const usv_match*)ctx->misc[0].p, n_cur, (const usv_match*)ctx->misc[1].p, n_old,
+                                         (int*)ctx->misc[2].p, cap, (long long*)ctx->misc[3].p, ctx->resolve_ws.p, ws, ctx->stream);
+  if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "id_matcher launch: %s", cudaGetErrorString(e));
+  ctx->launches += 2;
+  ctx->last_kernel = "id_matcher_write_kernel";
+  int64_t total = 0;
+  CU(cudaMemcpyAsync(&total, ctx->misc[3].p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const int64_t m = total < cap ? total : cap;
+  if (m > 0) CU(cudaMemcpy(h_out3, ctx->misc[2].p, sizeof(int32_t) * 3 * (size_t)m, cudaMemcpyDeviceToHost));
   *n_out = total;
   return USV_OK;
 }

@@ -143,4 +143,54 @@ cudaError_t launch_resolve(const usv_match* d_in, long long n, int skip_unmatche
   return cudaGetLastError();
 }
 
+// ---- IDMatcher, P/Main.cpp:483-499: join the current inter-frame matches with the previous ones on
+// cur.RightIndex == old.LeftIndex (:491), i-major / j-minor. The reference pushes `(Point3i)(cur, old.RightIndex)`
+// (:492): the comma operator keeps only old.RightIndex, so every triple is (old.RightIndex, 0, 0).
+// One thread per current match counts its partners, an exclusive scan places them, a second sweep writes them.
+__global__ void id_matcher_count_kernel(const usv_match* __restrict__ cur, uint32_t n_cur, const usv_match* __restrict__ old,
+                                        uint32_t n_old, uint32_t* __restrict__ cnt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cur) return;
+  const uint32_t key = cur[i].RightIndex;
+  uint32_t c = 0;
+  for (uint32_t j = 0; j < n_old; ++j) c += old[j].LeftIndex == key;
+  cnt[i] = c;
+}
+
+__global__ void id_matcher_write_kernel(const usv_match* __restrict__ cur, uint32_t n_cur, const usv_match* __restrict__ old,
+                                        uint32_t n_old, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pos,
+                                        int* __restrict__ out3, long long cap, long long* __restrict__ n_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cur) return;
+  const uint32_t key = cur[i].RightIndex;
+  long long o = pos[i];
+  for (uint32_t j = 0; j < n_old; ++j)
+    if (old[j].LeftIndex == key) {
+      if (o < cap) { out3[3 * o] = (int)old[j].RightIndex; out3[3 * o + 1] = 0; out3[3 * o + 2] = 0; }
+      ++o;
+    }
+  if (i == n_cur - 1) *n_out = (long long)pos[i] + cnt[i];
+}
+
+size_t id_matcher_workspace_bytes(long long n_cur) {
+  size_t scan_tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_cur);
+  return 2 * (size_t)n_cur * 4 + 512 + scan_tmp;
+}
+
+cudaError_t launch_id_matcher(const usv_match* d_cur, long long n_cur, const usv_match* d_old, long long n_old, int* d_out3,
+                              long long cap, long long* d_n_out, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+  if (n_cur == 0 || n_old == 0) return cudaMemsetAsync(d_n_out, 0, sizeof(long long), st);
+  uint32_t* cnt = (uint32_t*)d_ws;
+  uint32_t* pos = cnt + n_cur;
+  void* tmp = (void*)(((uintptr_t)(pos + n_cur) + 255) & ~(uintptr_t)255);
+  size_t tb = ws_bytes - ((char*)tmp - (char*)d_ws);
+  const int T = 128, B = (int)((n_cur + T - 1) / T);
+  id_matcher_count_kernel<<<B, T, 0, st>>>(d_cur, (uint32_t)n_cur, d_old, (uint32_t)n_old, cnt);
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, pos, (int)n_cur, st);
+  if (e != cudaSuccess) return e;
+  id_matcher_write_kernel<<<B, T, 0, st>>>(d_cur, (uint32_t)n_cur, d_old, (uint32_t)n_old, cnt, pos, d_out3, cap, d_n_out);
+  return cudaGetLastError();
+}
+
 }  // namespace usv

@@ -87,3 +87,41 @@ def gather_on_host(local, rank, world, group=None):
     if rank != 0:
         return None
     return {k: np.concatenate([b[k] for b in bucket], axis=0) for k in local}
+
+
+def extrapolated_distances(ctx, camera_side, this_frame, t_this, other_frames, t_other, templates, params):
+    """The reference's "unsynchronised" step for pixel templates: the other camera has no frame at
+    this camera's capture time, so the matched position of every template is tracked through the other camera's
+    last three frames and extrapolated to `t_this` before the disparity is taken
+    (MovingObjectDistanceCalculator, P/DistanceCalculator.cpp:53-84; call order of P/Main.cpp:1115-1143, :1238).
+
+    this_frame: [H, W] uint8; other_frames: (older, old, cur) [H, W] uint8 with timestamps t_other (seconds,
+    ascending); templates: [n, 2] int (x, y) window corners in this camera's frame.
+    Every step runs on the GPU: three sparse block searches (usv_match_templates_*) and the distance kernel
+    (usv_moving_object_distance). Returns dict(distance [n] f64 cm,
+    nearest_distance [n] f64 (disparity against the newest frame only), tracks [3, n] f32 x', accepted [n] bool).
+    """
+    tpl = np.ascontiguousarray(np.asarray(templates, np.int32).reshape(-1, 2))
+    n = len(tpl)
+    half_w, half_h = params.tmpl_w / 2.0, params.tmpl_h / 2.0
+    nxc = this_frame.shape[1] - params.tmpl_w + 1
+    tracks, ok = np.zeros((3, n), np.float32), np.ones(n, bool)
+    for k, fr in enumerate(other_frames):
+        got = ctx.match_templates(this_frame[None], fr[None], tpl[:, 0], tpl[:, 1], params, mask=_abi.OUT_RIGHT_INDEX)
+        ri = got["right_index"][0]
+        ok &= ri != _abi.NO_MATCH
+        tracks[k] = (ri % nxc).astype(np.float32)  # x' of the winner; y' = y (rectified pair)
+    centre = lambda xs: np.stack([xs + half_w, tpl[:, 1] + half_h], 1).astype(np.float32)  # noqa: E731
+    this_xy = centre(tpl[:, 0].astype(np.float32))
+    older_xy, old_xy, cur_xy = (centre(tracks[k]) for k in range(3))
+    # identity tracks: template i is object i in all three frames, so the index triples are (i, i, i) — what
+    # IDMatcher (P/Main.cpp:483-499, usv_id_matcher) is meant to deliver; the reference's own join collapses every
+    # triple to (old.RightIndex, 0, 0) through the comma operator at :492
+    idx3 = np.repeat(np.arange(n, dtype=np.int32)[:, None], 3, axis=1)
+    ns = lambda t: int(round(t * 1e9))  # noqa: E731
+    dist = ctx.moving_object_distance(camera_side, ns(t_this), this_xy, cur_xy, old_xy, older_xy, idx3,
+                                      ns(t_other[2]), ns(t_other[1]), ns(t_other[0]))
+    dist = np.where(ok, dist, np.inf) if len(dist) == n else np.full(n, np.inf)
+    disp_now = (tpl[:, 0] - tracks[2]).astype(np.int32) if camera_side == _abi.LEFT_CAM else (tracks[2] - tpl[:, 0]).astype(np.int32)
+    nearest = np.where(ok, ctx.disparity_to_distance(np.maximum(disp_now, 0), _abi.DIST_POWERLAW), np.inf)
+    return {"distance": dist, "nearest_distance": nearest, "tracks": tracks, "accepted": ok, "idx3": idx3}
