@@ -18,6 +18,9 @@
  *   distance_kind PINHOLE          -> inline disparity + pinhole        P/Main.cpp:681-694
  *   distance_kind POWERLAW         -> power-law fit                     P/DistanceCalculator.cpp:84
  *   usv_resolve_match_list         -> ResolveMatchList (whole list)     P/Main.cpp:432-477
+ *   usv_id_matcher                 -> IDMatcher                         P/Main.cpp:483-499
+ *   usv_preprocess_*               -> CalibrateLeft/RightImage, BGR2HSV,
+ *                                     LightingCorrection, BGR2GRAY      P/Main.cpp:351-371, 914-921
  *   usv_moving_object_distance     -> MovingObjectDistanceCalculator    P/DistanceCalculator.cpp:15-88
  *   usv_coordinate_position        -> CooridinatePositionCalculator     P/DistanceCalculator.cpp:90-141
  *   usv_pair_nearest / usv_stream_*-> CameraThread capture + timestamps P/Main.cpp:876-905
@@ -181,6 +184,33 @@ int usv_match_contours(usv_ctx *ctx, const int32_t *pts_this,
                        int32_t n_other, double accept_threshold,
                        usv_match *h_out, int64_t cap, int64_t *n_out,
                        double *h_cost_matrix);
+
+/* ---- the per-frame pre-pass before the matching path, P/Main.cpp:914-921 -------------
+ * camera frame (BGR, CV_8UC3) -> rectified, lighting-corrected gray frame (CV_8UC1):
+ *   remap(map1 CV_16SC2, map2 CV_16UC1, INTER_LINEAR, BORDER_CONSTANT 0)   CalibrateLeft/RightImage :351-359
+ *   BGR2HSV, equalizeHist(V), HSV2BGR                                      LightingCorrection :365-371, :919-920
+ *   BGR2GRAY                                                               :921
+ * OpenCV's arithmetic, bit for bit (oracle/preprocess_oracle.py states what is pinned against cv2 and how).
+ * maps: the fixed-point pair cv::initUndistortRectifyMap(..., CV_16SC2, ...) / cv::convertMaps produce, shared
+ * by all frames of the call; map1 == NULL skips the rectification. */
+#define USV_PRE_OPENCV3 3 /* the reference's library: 14-bit gray coefficients, unfused HSV2BGR products */
+#define USV_PRE_OPENCV4 4 /* cv2 4.13: 15-bit gray coefficients, fused `1 - s*h` (what the tests pin) */
+typedef struct usv_preprocess_params {
+  int32_t width, height;     /* source and destination size                         */
+  int32_t src_stride;        /* bytes between BGR rows                              */
+  int32_t dst_stride;        /* bytes between gray rows                             */
+  int64_t src_frame_stride;  /* bytes between frames of the batch                   */
+  int64_t dst_frame_stride;
+  int32_t flavour;           /* USV_PRE_OPENCV3 / USV_PRE_OPENCV4                   */
+  int32_t lighting;          /* 1: LightingCorrection (equalise V); 0: remap + gray */
+} usv_preprocess_params;
+int usv_preprocess_device(usv_ctx *ctx, const uint8_t *d_bgr, int32_t n_frames,
+                          const int16_t *d_map1, const uint16_t *d_map2,
+                          const usv_preprocess_params *params, uint8_t *d_gray,
+                          void *cuda_stream);
+int usv_preprocess_host(usv_ctx *ctx, const uint8_t *h_bgr, int32_t n_frames,
+                        const int16_t *h_map1, const uint16_t *h_map2,
+                        const usv_preprocess_params *params, uint8_t *h_gray);
 
 /* ---- ResolveMatchList, P/Main.cpp:432-477, on the GPU for lists of any length ----
  * One greedy pass in list order: a match overwrites every earlier tentative entry that shares LeftIndex

@@ -42,6 +42,16 @@ class FrameDesc(C.Structure):
     ]
 
 
+PRE_OPENCV3, PRE_OPENCV4 = 3, 4
+
+
+class PreprocessParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("src_stride", C.c_int32), ("dst_stride", C.c_int32),
+        ("src_frame_stride", C.c_int64), ("dst_frame_stride", C.c_int64), ("flavour", C.c_int32), ("lighting", C.c_int32),
+    ]
+
+
 class Outputs(C.Structure):
     _fields_ = [
         ("matches", C.c_void_p), ("right_index", C.c_void_p), ("raw_cost", C.c_void_p),

@@ -23,7 +23,7 @@ EXPORTS = (
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
     "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_wait",
     "usv_stream_bytes_per_pair", "usv_probe_issue_rate", "usv_match_contours",
-    "usv_resolve_match_list", "usv_resolve_match_list_device", "usv_id_matcher",
+    "usv_resolve_match_list", "usv_resolve_match_list_device", "usv_id_matcher", "usv_preprocess_device", "usv_preprocess_host",
 )
 
 
@@ -260,6 +260,27 @@ class Context:
         rc = lib().usv_id_matcher(self._h, _ptr(a), C.c_int64(len(a)), _ptr(b), C.c_int64(len(b)), _ptr(out), C.c_int64(len(out)), C.byref(n))
         self._check(rc, "usv_id_matcher")
         return out[:n.value]
+
+    def preprocess(self, bgr, map1=None, map2=None, lighting=True, flavour=_abi.PRE_OPENCV4, dst_align=16):
+        """The reference's pre-pass (P/Main.cpp:914-921) on the GPU: [n, H, W, 3] uint8 BGR frames (+ the fixed-point
+        rectification maps) -> [n, H, W] uint8 gray frames (a view on rows padded to `dst_align` bytes)."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        assert bgr.ndim == 4 and bgr.shape[3] == 3
+        n, h, w = bgr.shape[:3]
+        pitch = -(-w // dst_align) * dst_align
+        out = np.zeros((n, h, pitch), np.uint8)
+        p = _abi.PreprocessParams(w, h, 3 * w, pitch, 3 * w * h, pitch * h, int(flavour), int(bool(lighting)))
+        if map1 is not None:
+            map1 = np.ascontiguousarray(map1, np.int16).reshape(h, w, 2)
+            map2 = np.ascontiguousarray(map2, np.uint16).reshape(h, w)
+        rc = lib().usv_preprocess_host(self._h, _ptr(bgr), C.c_int32(n), _ptr(map1), _ptr(map2), C.byref(p), _ptr(out))
+        self._check(rc, "usv_preprocess_host")
+        return out[:, :, :w]
+
+    def preprocess_device(self, d_bgr, n_frames, d_map1, d_map2, params, d_gray, stream=0):
+        rc = lib().usv_preprocess_device(self._h, _ptr(d_bgr), C.c_int32(n_frames), _ptr(d_map1), _ptr(d_map2), C.byref(params),
+                                         _ptr(d_gray), C.c_void_p(int(stream)))
+        self._check(rc, "usv_preprocess_device")
 
     def probe_issue_rate(self, which=0, target_ms=20.0):
         """Sustained thread-instructions/s of VABSDIFF4.U8.ACC (0) / IDP.4A (1): the ALU roofline denominator."""

@@ -25,6 +25,10 @@ cudaError_t launch_resolve(const usv_match* d_in, long long n, int skip_unmatche
 size_t id_matcher_workspace_bytes(long long n_cur);
 cudaError_t launch_id_matcher(const usv_match* d_cur, long long n_cur, const usv_match* d_old, long long n_old, int* d_out3,
                               long long cap, long long* d_n_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
+size_t preprocess_scratch_bytes(int width, int height, int n_frames);
+cudaError_t launch_preprocess(int device, const uint8_t* d_src, uint8_t* d_dst, const short* d_map1, const uint16_t* d_map2, int n_frames,
+                              int width, int height, int src_stride, int dst_stride, long long src_frame_stride,
+                              long long dst_frame_stride, int flavour, int lighting, void* d_scratch, cudaStream_t st, int* n_launches);
 cudaError_t run_issue_probe(int which, int sms, double target_ms, double* lane_inst_per_s, uint32_t* d_scratch, cudaStream_t st);
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
 cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
@@ -52,7 +56,7 @@ struct usv_ctx {
   double* lut[3] = {nullptr, nullptr, nullptr};
   int lut_n[3] = {0, 0, 0};
   // grow-only scratch for the host paths
-  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws;
+  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws, pre_ws;
 };
 
 static const int kNumOut = 8;
@@ -198,6 +202,7 @@ extern "C" int usv_destroy(usv_ctx* ctx) {
   for (auto& b : ctx->out) if (b.p) cudaFree(b.p);
   for (auto& b : ctx->misc) if (b.p) cudaFree(b.p);
   if (ctx->resolve_ws.p) cudaFree(ctx->resolve_ws.p);
+  if (ctx->pre_ws.p) cudaFree(ctx->pre_ws.p);
   for (double* l : ctx->lut) if (l) cudaFree(l);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -441,6 +446,63 @@ extern "C" int usv_resolve_match_list(usv_ctx* ctx, const usv_match* h_in, int64
   const int64_t m = total < room ? total : room;
   if (m > 0) CU(cudaMemcpy(h_out, ctx->misc[1].p, sizeof(usv_match) * (size_t)m, cudaMemcpyDeviceToHost));
   *n_out = total;
+  return USV_OK;
+}
+
+// ---- pre-pass (usv_preprocess.cu) -------------------------------------------------------------
+static int preprocess_check(usv_ctx* ctx, int32_t n_frames, const usv_preprocess_params* p, const void* map1, const void* map2) {
+  if (!p) return fail(ctx, USV_ERR_INVALID_ARG, "null params");
+  if (n_frames < 0) return fail(ctx, USV_ERR_INVALID_ARG, "n_frames < 0");
+  if (p->width <= 0 || p->height <= 0 || p->width > 32767 || p->height > 32767) return fail(ctx, USV_ERR_INVALID_ARG, "bad frame size");
+  if (p->src_stride < 3 * p->width || p->dst_stride < p->width) return fail(ctx, USV_ERR_INVALID_ARG, "stride smaller than a row");
+  if (n_frames > 1 && (p->src_frame_stride < (int64_t)p->src_stride * p->height || p->dst_frame_stride < (int64_t)p->dst_stride * p->height))
+    return fail(ctx, USV_ERR_INVALID_ARG, "frame stride smaller than a frame");
+  if (p->flavour != USV_PRE_OPENCV3 && p->flavour != USV_PRE_OPENCV4) return fail(ctx, USV_ERR_INVALID_ARG, "unknown flavour %d", p->flavour);
+  if ((map1 == nullptr) != (map2 == nullptr)) return fail(ctx, USV_ERR_INVALID_ARG, "map1 and map2 come as a pair");
+  return USV_OK;
+}
+
+extern "C" int usv_preprocess_device(usv_ctx* ctx, const uint8_t* d_bgr, int32_t n_frames, const int16_t* d_map1, const uint16_t* d_map2,
+                                     const usv_preprocess_params* p, uint8_t* d_gray, void* cuda_stream) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  int rc = preprocess_check(ctx, n_frames, p, d_map1, d_map2);
+  if (rc) return rc;
+  if (n_frames == 0) return USV_OK;
+  if (!d_bgr || !d_gray) return fail(ctx, USV_ERR_INVALID_ARG, "null device pointer");
+  CU(cudaSetDevice(ctx->device));
+  if (p->lighting && (rc = grow(ctx, ctx->pre_ws, usv::preprocess_scratch_bytes(p->width, p->height, n_frames)))) return rc;
+  int nl = 0;
+  cudaError_t e = usv::launch_preprocess(ctx->device, d_bgr, d_gray, d_map1, d_map2, n_frames, p->width, p->height, p->src_stride,
+                                         p->dst_stride, p->src_frame_stride, p->dst_frame_stride, p->flavour, p->lighting,
+                                         ctx->pre_ws.p, (cudaStream_t)cuda_stream, &nl);
+  if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "preprocess launch: %s", cudaGetErrorString(e));
+  ctx->launches += nl;
+  ctx->last_kernel = p->lighting ? "rectify_hsv_hist_kernel+equalize_lut_kernel+hsv_gray_kernel" : "rectify_gray_kernel";
+  return USV_OK;
+}
+
+extern "C" int usv_preprocess_host(usv_ctx* ctx, const uint8_t* h_bgr, int32_t n_frames, const int16_t* h_map1, const uint16_t* h_map2,
+                                   const usv_preprocess_params* p, uint8_t* h_gray) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  int rc = preprocess_check(ctx, n_frames, p, h_map1, h_map2);
+  if (rc) return rc;
+  if (n_frames == 0) return USV_OK;
+  if (!h_bgr || !h_gray) return fail(ctx, USV_ERR_INVALID_ARG, "null host pointer");
+  CU(cudaSetDevice(ctx->device));
+  const size_t src_bytes = (size_t)(n_frames - 1) * p->src_frame_stride + (size_t)p->src_stride * p->height;
+  const size_t dst_bytes = (size_t)(n_frames - 1) * p->dst_frame_stride + (size_t)p->dst_stride * p->height;
+  const size_t px = (size_t)p->width * p->height;
+  if ((rc = up(ctx, ctx->misc[0], h_bgr, src_bytes))) return rc;
+  if ((rc = grow(ctx, ctx->misc[1], dst_bytes))) return rc;
+  if (h_map1) {
+    if ((rc = up(ctx, ctx->misc[2], h_map1, px * 4))) return rc;
+    if ((rc = up(ctx, ctx->misc[3], h_map2, px * 2))) return rc;
+  }
+  rc = usv_preprocess_device(ctx, (const uint8_t*)ctx->misc[0].p, n_frames, h_map1 ? (const int16_t*)ctx->misc[2].p : nullptr,
+                             h_map1 ? (const uint16_t*)ctx->misc[3].p : nullptr, p, (uint8_t*)ctx->misc[1].p, ctx->stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_gray, ctx->misc[1].p, dst_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return USV_OK;
 }
 
