@@ -77,6 +77,15 @@ void IDMatcher(std::vector<Match> InterframeMatchIndexes, std::vector<Match> Old
 int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,
                 const BlockSearchSpec& Spec, std::vector<Match>& ExportMatches, std::vector<double>& ExportDistances);
 
+// The reference's per-frame pre-pass as one GPU call (P/Main.cpp:914-921): CalibrateLeft/RightImage (:351-359,
+// remap with the fixed-point maps initUndistortRectifyMap(..., CV_16SC2, ...) produces), cvtColor BGR2HSV,
+// LightingCorrection (:365-371: equalizeHist on V, HSV2BGR) and cvtColor BGR2GRAY. `Map1` ([H][W][2] int16) and
+// `Map2` ([H][W] uint16) may both be null (already rectified frames). `Gray` must hold Height rows of GrayStep bytes.
+// OpenCV3Arithmetic = true reproduces the reference's library (14-bit gray coefficients, unfused HSV2BGR products),
+// false the OpenCV 4.13 arithmetic the tests pin against cv2. Returns 0 / -1 like the reference's thread functions.
+int RectifyLightingGray(const usv::ImageView& SrcBGR, const short* Map1, const unsigned short* Map2, bool Lighting,
+                        unsigned char* Gray, size_t GrayStep, bool OpenCV3Arithmetic = true, int Device = 0);
+
 // Last error text of the calling thread's GPU context ("" when none).
 const char* BlockSearchLastError();
 

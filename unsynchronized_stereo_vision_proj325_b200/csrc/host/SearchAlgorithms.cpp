@@ -166,6 +166,23 @@ void IDMatcher(std::vector<Match> InterframeMatchIndexes, std::vector<Match> Old
   for (int64_t k = 0; k < n; ++k) InterframeMatchIndexesComplete.push_back(cv::Point3i(out[3 * k], out[3 * k + 1], out[3 * k + 2]));
 }
 
+int RectifyLightingGray(const usv::ImageView& SrcBGR, const short* Map1, const unsigned short* Map2, bool Lighting, unsigned char* Gray,
+                        size_t GrayStep, bool OpenCV3Arithmetic, int Device) {
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  if (!SrcBGR.data || SrcBGR.channels != 3 || !Gray) { tc.last_error = "RectifyLightingGray: needs an 8UC3 frame and an output buffer"; return -1; }
+  usv_ctx* ctx = tc.get(Device);
+  if (!ctx) return -1;
+  usv_preprocess_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.width = SrcBGR.width; p.height = SrcBGR.height;
+  p.src_stride = (int32_t)SrcBGR.step; p.dst_stride = (int32_t)GrayStep;
+  p.src_frame_stride = (int64_t)SrcBGR.step * SrcBGR.height; p.dst_frame_stride = (int64_t)GrayStep * SrcBGR.height;
+  p.flavour = OpenCV3Arithmetic ? USV_PRE_OPENCV3 : USV_PRE_OPENCV4;
+  p.lighting = Lighting ? 1 : 0;
+  const int rc = usv_preprocess_host(ctx, SrcBGR.data, 1, Map1, Map2, &p, Gray);
+  return tc.check(ctx, rc, "usv_preprocess_host") ? 0 : -1;
+}
+
 int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,
                 const BlockSearchSpec& Spec, std::vector<Match>& ExportMatches, std::vector<double>& ExportDistances) {
   if (!ImportGrayThisCamera || !ImportGrayOtherCamera || !ImportGrayThisCamera->data || !ImportGrayOtherCamera->data ||

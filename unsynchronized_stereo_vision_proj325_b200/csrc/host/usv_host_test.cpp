@@ -104,6 +104,20 @@ int main(int argc, char** argv) {
   for (size_t k = 1; k < all.size(); ++k)  // i-major, j-minor order (P/Main.cpp:408-410)
     CHECK(all[k - 1].LeftIndex < all[k].LeftIndex || (all[k - 1].LeftIndex == all[k].LeftIndex && all[k - 1].RightIndex < all[k].RightIndex));
 
+  // ---- pre-pass: gray of a BGR frame, both arithmetic flavours (P/Main.cpp:921; 14-bit vs 15-bit coefficients)
+  {
+    std::vector<uint8_t> bgr(3 * 8 * 4), g3(8 * 4), g4(8 * 4);
+    for (size_t k = 0; k < bgr.size(); ++k) bgr[k] = (uint8_t)(37 * k + 11);
+    usv::ImageView v(bgr.data(), 8, 4, 3, 24);
+    CHECK(RectifyLightingGray(v, nullptr, nullptr, false, g3.data(), 8, true) == 0);
+    CHECK(RectifyLightingGray(v, nullptr, nullptr, false, g4.data(), 8, false) == 0);
+    for (int k = 0; k < 32; ++k) {
+      const int b = bgr[3 * k], g = bgr[3 * k + 1], r = bgr[3 * k + 2];
+      CHECK(g3[k] == ((b * 1868 + g * 9617 + r * 4899 + (1 << 13)) >> 14));
+      CHECK(g4[k] == ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15));
+    }
+  }
+
   // ---- DistanceCalculator known answers (reference code)
   {
     using tp = std::chrono::steady_clock::time_point;

@@ -45,12 +45,12 @@ __constant__ int c_hdiv[256];  // saturate_cast<int>((180 << 12) / (6. * i))
 __device__ __forceinline__ void remap_pixel(const PreJob& J, const uint8_t* __restrict__ src, int x, int y, int& b, int& g, int& r) {
   if (!J.map1) {
     const uint8_t* p = src + (long long)y * J.src_stride + 3 * x;
-    b = p[0]; g = p[1]; r = p[2];
+    b = __ldg(p); g = __ldg(p + 1); r = __ldg(p + 2);
     return;
   }
   const long long m = (long long)y * J.width + x;
-  const short2 xy = reinterpret_cast<const short2*>(J.map1)[m];
-  const int f = J.map2[m];
+  const short2 xy = __ldg(reinterpret_cast<const short2*>(J.map1) + m);
+  const int f = __ldg(J.map2 + m);
   const int fx = f & 31, fy = (f >> 5) & 31;
   int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
   if (w00 == 32768) { w00 = 32767; w11 = 1; }
@@ -59,7 +59,7 @@ __device__ __forceinline__ void remap_pixel(const PreJob& J, const uint8_t* __re
   auto tap = [&](int yy, int xx, int w) {
     if (w && yy >= 0 && yy < J.height && xx >= 0 && xx < J.width) {
       const uint8_t* p = src + (long long)yy * J.src_stride + 3 * xx;
-      acc[0] += w * p[0]; acc[1] += w * p[1]; acc[2] += w * p[2];
+      acc[0] += w * __ldg(p); acc[1] += w * __ldg(p + 1); acc[2] += w * __ldg(p + 2);
     }
   };
   tap(sy, sx, w00); tap(sy, sx + 1, w01); tap(sy + 1, sx, w10); tap(sy + 1, sx + 1, w11);
@@ -117,31 +117,44 @@ constexpr int kPrePix = 4;  // pixels per thread (consecutive in x): one 32-bit 
 
 // sweep 1 (lighting correction on): remap -> BGR2HSV -> HSV words + histogram of V
 __global__ void __launch_bounds__(kPreThreads) rectify_hsv_hist_kernel(const PreJob J) {
-  __shared__ uint32_t s_hist[256];
+  // eight copies of the histogram, picked by lane: neighbouring pixels have similar V, and shared-memory atomics
+  // on one address serialise
+  __shared__ uint32_t s_hist[256 * 8];
   const int frame = blockIdx.y;
-  for (int i = threadIdx.x; i < 256; i += kPreThreads) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < 256 * 8; i += kPreThreads) s_hist[i] = 0;
   __syncthreads();
+  const uint32_t copy = threadIdx.x & 7;
   const uint8_t* src = J.src + (long long)frame * J.src_frame_stride;
   uint32_t* hsv = J.hsv + (long long)frame * J.width * J.height;
-  const int groups_per_row = (J.width + kPrePix - 1) / kPrePix;
-  const long long n_groups = (long long)groups_per_row * J.height;
-  for (long long gi = (long long)blockIdx.x * kPreThreads + threadIdx.x; gi < n_groups; gi += (long long)gridDim.x * kPreThreads) {
-    const int y = (int)(gi / groups_per_row), x0 = (int)(gi - (long long)y * groups_per_row) * kPrePix;
+  const uint32_t groups_per_row = (uint32_t)(J.width + kPrePix - 1) / kPrePix;
+  const uint32_t n_groups = groups_per_row * (uint32_t)J.height;  // < 2^31: width, height <= 32767 (checked by the caller)
+  for (uint32_t gi = blockIdx.x * kPreThreads + threadIdx.x; gi < n_groups; gi += gridDim.x * kPreThreads) {
+    const uint32_t yu = gi / groups_per_row;
+    const int y = (int)yu, x0 = (int)(gi - yu * groups_per_row) * kPrePix;
+    // all gathers of the group first (independent loads in flight), then the arithmetic, stores and atomics
+    int b[kPrePix], g[kPrePix], r[kPrePix];
+#pragma unroll
+    for (int k = 0; k < kPrePix; ++k) {
+      b[k] = g[k] = r[k] = 0;
+      if (x0 + k < J.width) remap_pixel(J, src, x0 + k, y, b[k], g[k], r[k]);
+    }
 #pragma unroll
     for (int k = 0; k < kPrePix; ++k) {
       const int x = x0 + k;
       if (x < J.width) {
-        int b, g, r;
-        remap_pixel(J, src, x, y, b, g, r);
-        const uint32_t w = bgr2hsv_word(b, g, r);
+        const uint32_t w = bgr2hsv_word(b[k], g[k], r[k]);
         hsv[(long long)y * J.width + x] = w;
-        atomicAdd(&s_hist[w >> 16], 1u);
+        atomicAdd(&s_hist[(w >> 16) * 8 + copy], 1u);
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 256; i += kPreThreads)
-    if (s_hist[i]) atomicAdd(&J.hist[frame * 256 + i], s_hist[i]);
+  for (int i = threadIdx.x; i < 256; i += kPreThreads) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c += s_hist[i * 8 + k];
+    if (c) atomicAdd(&J.hist[frame * 256 + i], c);
+  }
 }
 
 // cv::equalizeHist's LUT (histogram.cpp): lut[first] = 0, lut[i] = saturate_cast<uchar>(cumsum * scale),
@@ -183,10 +196,11 @@ __global__ void __launch_bounds__(kPreThreads) hsv_gray_kernel(const PreJob J) {
   __syncthreads();
   const uint32_t* hsv = J.hsv + (long long)frame * J.width * J.height;
   uint8_t* dst = J.dst + (long long)frame * J.dst_frame_stride;
-  const int groups_per_row = (J.width + kPrePix - 1) / kPrePix;
-  const long long n_groups = (long long)groups_per_row * J.height;
-  for (long long gi = (long long)blockIdx.x * kPreThreads + threadIdx.x; gi < n_groups; gi += (long long)gridDim.x * kPreThreads) {
-    const int y = (int)(gi / groups_per_row), x0 = (int)(gi - (long long)y * groups_per_row) * kPrePix;
+  const uint32_t groups_per_row = (uint32_t)(J.width + kPrePix - 1) / kPrePix;
+  const uint32_t n_groups = groups_per_row * (uint32_t)J.height;  // < 2^31: width, height <= 32767 (checked by the caller)
+  for (uint32_t gi = blockIdx.x * kPreThreads + threadIdx.x; gi < n_groups; gi += gridDim.x * kPreThreads) {
+    const uint32_t yu = gi / groups_per_row;
+    const int y = (int)yu, x0 = (int)(gi - yu * groups_per_row) * kPrePix;
     uint32_t packed = 0;
 #pragma unroll
     for (int k = 0; k < kPrePix; ++k) {
@@ -209,10 +223,11 @@ __global__ void __launch_bounds__(kPreThreads) rectify_gray_kernel(const PreJob 
   const int frame = blockIdx.y;
   const uint8_t* src = J.src + (long long)frame * J.src_frame_stride;
   uint8_t* dst = J.dst + (long long)frame * J.dst_frame_stride;
-  const int groups_per_row = (J.width + kPrePix - 1) / kPrePix;
-  const long long n_groups = (long long)groups_per_row * J.height;
-  for (long long gi = (long long)blockIdx.x * kPreThreads + threadIdx.x; gi < n_groups; gi += (long long)gridDim.x * kPreThreads) {
-    const int y = (int)(gi / groups_per_row), x0 = (int)(gi - (long long)y * groups_per_row) * kPrePix;
+  const uint32_t groups_per_row = (uint32_t)(J.width + kPrePix - 1) / kPrePix;
+  const uint32_t n_groups = groups_per_row * (uint32_t)J.height;  // < 2^31: width, height <= 32767 (checked by the caller)
+  for (uint32_t gi = blockIdx.x * kPreThreads + threadIdx.x; gi < n_groups; gi += gridDim.x * kPreThreads) {
+    const uint32_t yu = gi / groups_per_row;
+    const int y = (int)yu, x0 = (int)(gi - yu * groups_per_row) * kPrePix;
     uint32_t packed = 0;
 #pragma unroll
     for (int k = 0; k < kPrePix; ++k) {
