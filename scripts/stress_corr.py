@@ -1,0 +1,49 @@
+"""Randomised parity stress of the sliding-window correlation kernel (NCC / ZNCC, gray and colour) against the CPU oracle:
+bit-exact indices, disparities, f64 scores and MatchValues.  python scripts/stress_corr.py [n_cases] [seed]"""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+from unsynchronized_stereo_vision_proj325_b200 import _abi, api, synth
+from oracle import oracle
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+ctx = api.Context(0)
+bad = dense = 0
+for t in range(n_cases):
+    tw = int(rng.choice([8, 12, 16, 24, 32]))
+    th = int(rng.choice([1, 4, 8, 13, 16, 24, 32]))
+    c = int(rng.choice([1, 3]))
+    w = int(rng.integers(tw, 200))
+    h = int(rng.integers(th, th + 40))
+    n = int(rng.integers(1, 3))
+    side = int(rng.integers(0, 2))
+    lo = 0 if rng.random() < 0.4 else int(rng.integers(-20, 40))
+    hi = lo + int(rng.integers(0, 150)) if rng.random() < 0.8 else 1 << 20
+    thr = float(rng.choice([0.75, 0.2, 2.5]))
+    shift = int(rng.integers(-20, 40))
+    left, right = synth.make_pairs(n, w, h, c, shift=shift if abs(shift) < w else 0, noise_sigma=float(rng.choice([0, 2.0])), seed=2000 + t)
+    mode = rng.random()
+    if mode < 0.1:
+        left[:] = 90; right[:] = 90                      # flat: zero variance everywhere (score 0, all ties)
+    elif mode < 0.25:
+        left[:, : h // 2] = 200; right[:, :, : w // 2] = 17   # flat regions next to texture
+    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=str(rng.choice(["ncc", "zncc"])), search_min=lo, search_max=hi, camera_side=side,
+                         accept_threshold=thr, distance_kind=int(rng.integers(0, 3)))
+    got = ctx.match_dense(left, right, p)
+    dense += ctx.last_kernel == "dense_corr_argmin_kernel"
+    exp = oracle.match_dense(left, right, p)
+    ok = all(np.array_equal(got[k], exp[k]) for k in ("right_index", "raw_cost", "disparity_u16"))
+    ok = ok and got["matches"].tobytes() == exp["matches"].tobytes() and got["score"].tobytes() == exp["score"].tobytes()
+    if not ok:
+        bad += 1
+        nb = int((got["right_index"] != exp["right_index"]).sum())
+        ns = int((got["score"].view(np.uint64) != exp["score"].view(np.uint64)).sum())
+        print("MISMATCH case", t, dict(w=w, h=h, c=c, n=n, tw=tw, th=th, side=side, lo=lo, hi=hi, kind=p.cost_kind, mode=round(mode, 2)), ctx.last_kernel,
+              "index diffs", nb, "score diffs", ns, flush=True)
+        if bad <= 3:
+            ii = np.argwhere(got["right_index"] != exp["right_index"])[:4]
+            for a in ii:
+                print("   win", a.tolist(), "got", got["right_index"][tuple(a)], got["score"][tuple(a)], "exp", exp["right_index"][tuple(a)], exp["score"][tuple(a)])
+print("cases %d, on the sliding correlation kernel %d, mismatches %d" % (n_cases, dense, bad))
+sys.exit(1 if bad else 0)

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -17,6 +18,9 @@ namespace usv {
 cudaError_t launch_direct(const DevJob& J, int n_pairs, cudaStream_t st);
 // returns cudaErrorNotSupported when the dense kernels do not cover the job
 cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches);
+size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out);
+cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
+                              int* n_launches);
 cudaError_t launch_contour_descriptors(const int* pts, const int* off, int n, double* desc, cudaStream_t st);
 cudaError_t launch_contour_costs(const double* dl, int nl, const double* dr, int nr, double* cost, cudaStream_t st);
 size_t resolve_workspace_bytes(long long n);
@@ -56,7 +60,7 @@ struct usv_ctx {
   double* lut[3] = {nullptr, nullptr, nullptr};
   int lut_n[3] = {0, 0, 0};
   // grow-only scratch for the host paths
-  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws, pre_ws;
+  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws, pre_ws, corr_ws;
 };
 
 static const int kNumOut = 8;
@@ -203,6 +207,7 @@ extern "C" int usv_destroy(usv_ctx* ctx) {
   for (auto& b : ctx->misc) if (b.p) cudaFree(b.p);
   if (ctx->resolve_ws.p) cudaFree(ctx->resolve_ws.p);
   if (ctx->pre_ws.p) cudaFree(ctx->pre_ws.p);
+  if (ctx->corr_ws.p) cudaFree(ctx->corr_ws.p);
   for (double* l : ctx->lut) if (l) cudaFree(l);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -267,6 +272,22 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
     }
     if (e != cudaErrorNotSupported) return fail(ctx, USV_ERR_CUDA, "dense launch: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
+    if (p->cost_kind == USV_COST_NCC || p->cost_kind == USV_COST_ZNCC) {
+      // sliding-window correlation kernel: planes + window statistics live in a scratch buffer, pairs run in chunks
+      const size_t per_pair = usv::corr_scratch_bytes_per_pair(J, nullptr);
+      const size_t cap = (size_t)3 << 29;  // 1.5 GB
+      size_t want = per_pair * (size_t)n_pairs;
+      if (want > cap) want = std::max(per_pair, cap / per_pair * per_pair);
+      if ((rc = grow(ctx, ctx->corr_ws, want))) return rc;
+      e = usv::launch_dense_corr(J, n_pairs, ctx->corr_ws.p, ctx->corr_ws.cap, st, &name, &nl);
+      if (e == cudaSuccess) {
+        ctx->launches += nl;
+        ctx->last_kernel = name;
+        return USV_OK;
+      }
+      if (e != cudaErrorNotSupported) return fail(ctx, USV_ERR_CUDA, "dense correlation launch: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
   }
   cudaError_t e = usv::launch_direct(J, n_pairs, st);
   if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "direct launch: %s", cudaGetErrorString(e));
