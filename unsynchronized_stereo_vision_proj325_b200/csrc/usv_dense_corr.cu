@@ -31,7 +31,7 @@
 namespace usv {
 
 constexpr int kCThreads = 128;
-constexpr int kCRB = 4;           // rows per staging block
+constexpr int kCRB = 2;           // rows per staging block (rows are long here: a barrier every other row is cheap)
 constexpr int kCLW = 32;          // words per L copy row
 constexpr int kCRW = 44;          // words per R copy row (40 used)
 constexpr int kCRowWords = 4 * kCLW + 4 * kCRW;
@@ -250,7 +250,7 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
 }
 
 template <int DIR, int NW, int NPL>
-__global__ void __launch_bounds__(kCThreads, 2) dense_corr_argmin_kernel(const DevJob J, const CorrCfg cfg) {
+__global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const DevJob J, const CorrCfg cfg) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* s_ring = smem_u32;                                              // [2][2*kCRB][NPL][kCRowWords]
   double* s_bsc = reinterpret_cast<double*>(smem_u32 + 4 * kCRB * NPL * kCRowWords);  // [bh][128] best score
@@ -313,29 +313,46 @@ __global__ void corr_planes_kernel(const uint8_t* __restrict__ src, long long sr
     for (int c = 0; c < channels; ++c) d[(long long)c * plane_stride + x] = x < width ? s[x * channels + c] : 0;
 }
 
-// window statistics of one camera: thread = (window column x, band of rows); vertical sliding sums of the row-window
-// sums. out[y][x] = (left ? -Sa : Sb, 1/sqrt(var)) with the oracle's operations (usv_common.cuh ncc_score / zncc_score).
-__global__ void corr_stats_kernel(const uint8_t* __restrict__ frames, long long frame_stride, int row_stride, int channels, int tw, int th,
-                                  int nxc, int nyc, int kind, int is_left, int band_rows, double2* __restrict__ out) {
+// Window statistics of one camera in two sliding stages (a few loads per window instead of 2 * tw * C):
+//   corr_rowsum_kernel  rs[y][x] = (sum, sum of squares) of the tw * C bytes of row y starting at pixel x; a thread
+//                       owns a run of 32 consecutive x of one row and slides: + the C bytes entering, - the C leaving
+//   corr_stats_kernel   vertical sliding sum of th rows of rs -> (left ? -Sa : Sb, 1/sqrt(variance term)) with the
+//                       oracle's operations (usv_common.cuh ncc_score / zncc_score); thread = (x, band of rows)
+__global__ void corr_rowsum_kernel(const uint8_t* __restrict__ frames, long long frame_stride, int row_stride, int channels, int tw,
+                                   int nxc, int height, uint2* __restrict__ rs) {
+  const int run = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, pair = blockIdx.z;
+  const int xa = run * 32;
+  if (xa >= nxc) return;
+  const int xb = min(xa + 32, nxc);
+  const uint8_t* r = frames + (long long)pair * frame_stride + (long long)y * row_stride;
+  const int nb = tw * channels;
+  uint32_t s1 = 0, s2 = 0;
+  for (int k = 0; k < nb; ++k) { const uint32_t v = __ldg(r + xa * channels + k); s1 += v; s2 += v * v; }
+  uint2* o = rs + ((long long)pair * height + y) * nxc;
+  for (int x = xa; x < xb; ++x) {
+    o[x] = make_uint2(s1, s2);
+    if (x + 1 < xb)
+      for (int c = 0; c < channels; ++c) {
+        const uint32_t vin = __ldg(r + (x + tw) * channels + c), vout = __ldg(r + x * channels + c);
+        s1 += vin - vout; s2 += vin * vin - vout * vout;
+      }
+  }
+}
+
+__global__ void corr_stats_kernel(const uint2* __restrict__ rs, int height, int tw, int th, int channels, int nxc, int nyc, int kind,
+                                  int is_left, int band_rows, double2* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int pair = blockIdx.z;
   if (x >= nxc) return;
   const int y0 = blockIdx.y * band_rows, y1 = min(y0 + band_rows, nyc);
-  const uint8_t* f = frames + (long long)pair * frame_stride + (long long)x * channels;
-  const int nb = tw * channels;
+  const uint2* col = rs + (long long)pair * height * nxc + x;
   const long long n = (long long)tw * th * channels;
-  auto row_sums = [&](int y, uint32_t& s1, uint32_t& s2) {
-    const uint8_t* r = f + (long long)y * row_stride;
-    uint32_t a = 0, b = 0;
-    for (int k = 0; k < nb; ++k) { const uint32_t v = __ldg(r + k); a += v; b += v * v; }
-    s1 = a; s2 = b;
-  };
   long long sa = 0, saa = 0;
-  for (int v = 0; v < th - 1; ++v) { uint32_t s1, s2; row_sums(y0 + v, s1, s2); sa += s1; saa += s2; }
+  for (int v = 0; v < th - 1; ++v) { const uint2 q = __ldg(col + (long long)(y0 + v) * nxc); sa += q.x; saa += q.y; }
   for (int y = y0; y < y1; ++y) {
-    uint32_t s1, s2;
-    row_sums(y + th - 1, s1, s2);
-    sa += s1; saa += s2;
+    const uint2 qin = __ldg(col + (long long)(y + th - 1) * nxc);
+    sa += qin.x; saa += qin.y;
     double m, r;
     if (kind == USV_COST_NCC) {
       m = 0.0;
@@ -346,8 +363,8 @@ __global__ void corr_stats_kernel(const uint8_t* __restrict__ frames, long long 
       r = da == 0 ? 0.0 : __drcp_rn(__dsqrt_rn((double)da));
     }
     out[((long long)pair * nyc + y) * nxc + x] = make_double2(m, r);
-    row_sums(y, s1, s2);
-    sa -= s1; saa -= s2;
+    const uint2 qout = __ldg(col + (long long)y * nxc);
+    sa -= qout.x; saa -= qout.y;
   }
 }
 
@@ -355,7 +372,7 @@ size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out) {
   const int pitch = ((J.width + 15) & ~15) + 16;
   if (pitch_out) *pitch_out = pitch;
   const size_t planes = J.channels > 1 ? 2ull * J.channels * J.height * pitch : 0;
-  return planes + 2ull * J.nyc * J.nxc * sizeof(double2) + 256;
+  return planes + 2ull * J.nyc * J.nxc * sizeof(double2) + (size_t)J.height * J.nxc * sizeof(uint2) + 512;
 }
 
 // Returns cudaErrorNotSupported when the job is outside the kernel's coverage (the caller then runs the direct form).
@@ -381,7 +398,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   cfg.n_eff = J.cost_kind == USV_COST_ZNCC ? (double)J.n_elems : 1.0;
   const int npl = J.channels;
   const size_t ring_bytes = (size_t)4 * kCRB * npl * kCRowWords * 4;
-  const size_t smem_budget = 110 * 1024;  // two CTAs per SM
+  const size_t smem_budget = 74 * 1024;  // three CTAs per SM
   int bh_max = (int)((smem_budget - ring_bytes) / (128 * 12));
   if (bh_max < 8) return cudaErrorNotSupported;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
@@ -414,12 +431,16 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     base = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
     double2* st_l = (double2*)base;
     double2* st_r = st_l + (size_t)np * J.nyc * J.nxc;
+    uint2* rsum = (uint2*)(st_r + (size_t)np * J.nyc * J.nxc);  // [np][H][nxc], reused for the right camera
     {
-      const int band_rows = 32;
-      const dim3 g((J.nxc + 127) / 128, (J.nyc + band_rows - 1) / band_rows, np);
-      corr_stats_kernel<<<g, 128, 0, st>>>(fl, J.frame_stride, J.row_stride, J.channels, J.tw, J.th, J.nxc, J.nyc, J.cost_kind, 1, band_rows, st_l);
-      corr_stats_kernel<<<g, 128, 0, st>>>(fr, J.frame_stride, J.row_stride, J.channels, J.tw, J.th, J.nxc, J.nyc, J.cost_kind, 0, band_rows, st_r);
-      *n_launches += 2;
+      const int band_rows = 64;
+      const dim3 g1(((J.nxc + 31) / 32 + 63) / 64, J.height, np);
+      const dim3 g2((J.nxc + 127) / 128, (J.nyc + band_rows - 1) / band_rows, np);
+      corr_rowsum_kernel<<<g1, 64, 0, st>>>(fl, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.height, rsum);
+      corr_stats_kernel<<<g2, 128, 0, st>>>(rsum, J.height, J.tw, J.th, J.channels, J.nxc, J.nyc, J.cost_kind, 1, band_rows, st_l);
+      corr_rowsum_kernel<<<g1, 64, 0, st>>>(fr, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.height, rsum);
+      corr_stats_kernel<<<g2, 128, 0, st>>>(rsum, J.height, J.tw, J.th, J.channels, J.nxc, J.nyc, J.cost_kind, 0, band_rows, st_r);
+      *n_launches += 4;
     }
     cfg.stat_l = st_l; cfg.stat_r = st_r;
     cfg.pair0 = p0;
