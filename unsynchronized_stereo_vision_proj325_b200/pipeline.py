@@ -31,7 +31,8 @@ def default_matcher(ctx, frame, params, pairs_per_slot, n_slots, mask):
 
 
 def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0 / 60.0, rank=0, world=1, ctx=None,
-                  pairs_per_slot=16, n_slots=3, mask=_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST, stream_factory=default_matcher):
+                  pairs_per_slot=16, n_slots=3, mask=_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST, stream_factory=default_matcher,
+                  copy_threads=1):
     """Pair two unsynchronised streams and match this rank's shard of the pairs.
 
     frames_*: [n, H, W(, C)] uint8 arrays (host) indexed by frame number; t_*: ascending timestamps.
@@ -49,6 +50,10 @@ def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0
     st = stream_factory(ctx, frame, params, pairs_per_slot, n_slots, mask)
     outs = {name: [] for name, bit, _ in _abi.OUTPUT_FIELDS if mask & bit}
     pending = []  # (slot, count) in submission order
+    pool = None
+    if copy_threads > 1:  # the "capture" memcpy into the pinned ring is the host-side bound of the stream: spread it
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(copy_threads)
 
     def drain_one():
         slot, cnt = pending.pop(0)
@@ -62,13 +67,20 @@ def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0
             drain_one()  # the oldest in-flight batch owns this slot
         cnt = min(pairs_per_slot, n - b0)
         # "capture": the paired frames land in the slot's pinned buffers
-        st.slots[slot]["left"][:cnt] = frames_left[li[b0:b0 + cnt]].reshape(cnt, h, w * c)
-        st.slots[slot]["right"][:cnt] = frames_right[ri[b0:b0 + cnt]].reshape(cnt, h, w * c)
+        sl, sr = st.slots[slot]["left"], st.slots[slot]["right"]
+        if pool is None:
+            sl[:cnt] = frames_left[li[b0:b0 + cnt]].reshape(cnt, h, w * c)
+            sr[:cnt] = frames_right[ri[b0:b0 + cnt]].reshape(cnt, h, w * c)
+        else:
+            list(pool.map(lambda k: (np.copyto(sl[k], frames_left[li[b0 + k]].reshape(h, w * c)),
+                                     np.copyto(sr[k], frames_right[ri[b0 + k]].reshape(h, w * c))), range(cnt)))
         st.submit(slot, cnt)
         pending.append((slot, cnt))
     while pending:
         drain_one()
     st.close()
+    if pool is not None:
+        pool.shutdown()
     res = {"pair_left": li, "pair_right": ri, "dt": dt}
     for k, v in outs.items():
         res[k] = np.concatenate(v, axis=0) if v else np.zeros((0, 0), dtype=dict((n_, d) for n_, _, d in _abi.OUTPUT_FIELDS)[k])
