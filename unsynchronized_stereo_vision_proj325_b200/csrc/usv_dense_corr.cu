@@ -61,7 +61,7 @@ __device__ __forceinline__ bool corr_better(double sc_o, int x_o, double sc_m, i
   return vo < vm || (vo == vm && x_o < x_m);
 }
 
-template <int DIR, int NW, int NPL>
+template <int DIR, int NW, int NPL, bool SSD>
 __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, uint32_t* s_ring, double* s_bsc, int* s_bx,
                                           const uint8_t* __restrict__ Lb, const uint8_t* __restrict__ Rb, const double2* __restrict__ stl,
                                           const double2* __restrict__ str, const int X0, const int XR0, const int dbase, const int y0,
@@ -166,7 +166,7 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
       for (int k = 0; k < 11; ++k) {
         const int xk = xrb + 4 * k;
         Rs[k] = __ldg(rs + min(max(xk, 0), J.nxc - 1));
-        if (xk < 0 || xk > J.nxc - 1) Rs[k].y = nan;  // a candidate outside the frame loses every comparison
+        if (xk < 0 || xk > J.nxc - 1) { Rs[k].y = nan; if (SSD) Rs[k].x = nan; }  // a candidate outside the frame loses every comparison
       }
       // halo columns 8 .. 8+NW-2 from the next u-lane; window sums of column 0
       uint32_t Hx[NW - 1][4], T[4];
@@ -189,8 +189,10 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
         for (int j = 0; j < 4; ++j) {
           const int k = DIR < 0 ? i - j + 3 : i + j;
           const double nsab = __fma_rn(nj[j], __hiloint2double(0x43300000, (int)T[j]), c0j[j]);  // n * Sab, exact
-          const double num = __fma_rn(La[i].x, Rs[k].x, nsab);                                     // - Sa * Sb, exact
-          const double sc = __dmul_rn(__dmul_rn(num, La[i].y), Rs[k].y);
+          // ZNCC / NCC: n Sab - Sa Sb (exact), then the oracle's two roundings. SSD: "score" = -(Saa + Sbb - 2 Sab), an
+          // exact integer, so v = 1 - score = 1 + SSD orders the candidates by their integer cost
+          const double num = SSD ? __dadd_rn(__dadd_rn(La[i].x, Rs[k].x), nsab) : __fma_rn(La[i].x, Rs[k].x, nsab);
+          const double sc = SSD ? num : __dmul_rn(__dmul_rn(num, La[i].y), Rs[k].y);
           const double v = __dsub_rn(1.0, sc);
           // j ascending = x' descending (LeftCam) / ascending (RightCam): on a tie the smaller x' stays
           const bool take = DIR < 0 ? v <= best_v : v < best_v;
@@ -249,7 +251,7 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
   }
 }
 
-template <int DIR, int NW, int NPL>
+template <int DIR, int NW, int NPL, bool SSD>
 __global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const DevJob J, const CorrCfg cfg) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* s_ring = smem_u32;                                              // [2][2*kCRB][NPL][kCRowWords]
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const D
     const int D0 = d_lo + 32 * pass;
     const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
-    corr_pass<DIR, NW, NPL>(J, cfg, s_ring, s_bsc, s_bx, Lb, Rb, stl, str, X0, XR0, dbase, y0, rows_in);
+    corr_pass<DIR, NW, NPL, SSD>(J, cfg, s_ring, s_bsc, s_bx, Lb, Rb, stl, str, X0, XR0, dbase, y0, rows_in);
   }
   __syncthreads();
 
@@ -298,7 +300,10 @@ __global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const D
     const long long w = (long long)y * J.nx + x;
     const long long g = (long long)(cfg.pair0 + pair) * J.n_templates + w;
     if (xr == kNoX) write_result(J, g, (uint32_t)w, x, y, -1, 0xffffffffu, 0.0, __longlong_as_double(0x7ff0000000000000ll));
-    else write_result(J, g, (uint32_t)w, x, y, xr, 0xffffffffu, __dadd_rn(sc, 0.0), __dsub_rn(1.0, sc));  // -0.0 -> 0.0 (flat windows)
+    else if (SSD) {
+      const uint32_t raw = (uint32_t)(-sc);
+      write_result(J, g, (uint32_t)w, x, y, xr, raw, 0.0, normalised_cost(raw, USV_COST_SSD, J.n_elems));
+    } else write_result(J, g, (uint32_t)w, x, y, xr, 0xffffffffu, __dadd_rn(sc, 0.0), __dsub_rn(1.0, sc));  // -0.0 -> 0.0 (flat windows)
   }
 }
 
@@ -354,7 +359,10 @@ __global__ void corr_stats_kernel(const uint2* __restrict__ rs, int height, int 
     const uint2 qin = __ldg(col + (long long)(y + th - 1) * nxc);
     sa += qin.x; saa += qin.y;
     double m, r;
-    if (kind == USV_COST_NCC) {
+    if (kind == USV_COST_SSD) {
+      m = -(double)saa;  // both cameras: score = 2 Sab - Saa - Sbb
+      r = 1.0;
+    } else if (kind == USV_COST_NCC) {
       m = 0.0;
       r = saa == 0 ? 0.0 : __drcp_rn(__dsqrt_rn((double)saa));
     } else {
@@ -380,7 +388,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
                               int* n_launches) {
   *n_launches = 0;
   if (J.tx || J.sx != 1 || J.sy != 1) return cudaErrorNotSupported;
-  if (J.cost_kind != USV_COST_NCC && J.cost_kind != USV_COST_ZNCC) return cudaErrorNotSupported;
+  if (J.cost_kind != USV_COST_NCC && J.cost_kind != USV_COST_ZNCC && J.cost_kind != USV_COST_SSD) return cudaErrorNotSupported;
   if (J.channels != 1 && J.channels != 3) return cudaErrorNotSupported;
   const int nw = J.tw / 4;
   if (J.tw % 4 != 0 || !(nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) || J.th > 64) return cudaErrorNotSupported;
@@ -395,7 +403,8 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   cfg.stride_px = 4 * (32 - nw + 1);
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
   cfg.x_off = J.camera_side == USV_LEFT_CAM ? ((cfg.n_xtiles * cfg.stride_px - J.nxc) & ~3) : 0;
-  cfg.n_eff = J.cost_kind == USV_COST_ZNCC ? (double)J.n_elems : 1.0;
+  cfg.n_eff = J.cost_kind == USV_COST_ZNCC ? (double)J.n_elems : J.cost_kind == USV_COST_SSD ? 2.0 : 1.0;
+  const bool ssd = J.cost_kind == USV_COST_SSD;
   const int npl = J.channels;
   const size_t ring_bytes = (size_t)4 * kCRB * npl * kCRowWords * 4;
   const size_t smem_budget = 74 * 1024;  // three CTAs per SM
@@ -447,7 +456,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     const dim3 grid(cfg.n_xtiles, cfg.n_bands, np), block(kCThreads);
 #define USV_CORR_LAUNCH(D, NWW, NPLL)                                                                      \
   {                                                                                                        \
-    auto kfn = dense_corr_argmin_kernel<D, NWW, NPLL>;                                                     \
+    auto kfn = ssd ? dense_corr_argmin_kernel<D, NWW, NPLL, true> : dense_corr_argmin_kernel<D, NWW, NPLL, false>; \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e != cudaSuccess) return e;                                                                        \
     kfn<<<grid, block, smem, st>>>(J, cfg);                                                                \
