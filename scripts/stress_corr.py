@@ -1,4 +1,4 @@
-"""Randomised parity stress of the sliding-window correlation kernel (NCC / ZNCC, gray and colour) against the CPU oracle:
+"""Randomised parity stress of the sliding-window correlation kernel (NCC / ZNCC / SSD, gray and colour; SAD on colour frames) against the CPU oracle:
 bit-exact indices, disparities, f64 scores and MatchValues.  python scripts/stress_corr.py [n_cases] [seed]"""
 import sys
 import numpy as np
@@ -28,10 +28,10 @@ for t in range(n_cases):
         left[:] = 90; right[:] = 90                      # flat: zero variance everywhere (score 0, all ties)
     elif mode < 0.25:
         left[:, : h // 2] = 200; right[:, :, : w // 2] = 17   # flat regions next to texture
-    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=str(rng.choice(["ncc", "zncc"])), search_min=lo, search_max=hi, camera_side=side,
+    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=str(rng.choice(["ncc", "zncc", "ssd", "sad"])), search_min=lo, search_max=hi, camera_side=side,
                          accept_threshold=thr, distance_kind=int(rng.integers(0, 3)))
     got = ctx.match_dense(left, right, p)
-    dense += ctx.last_kernel == "dense_corr_argmin_kernel"
+    dense += ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_sad_argmin_kernel")  # gray SAD has its own kernel
     exp = oracle.match_dense(left, right, p)
     ok = all(np.array_equal(got[k], exp[k]) for k in ("right_index", "raw_cost", "disparity_u16"))
     ok = ok and got["matches"].tobytes() == exp["matches"].tobytes() and got["score"].tobytes() == exp["score"].tobytes()
@@ -45,5 +45,5 @@ for t in range(n_cases):
             ii = np.argwhere(got["right_index"] != exp["right_index"])[:4]
             for a in ii:
                 print("   win", a.tolist(), "got", got["right_index"][tuple(a)], got["score"][tuple(a)], "exp", exp["right_index"][tuple(a)], exp["score"][tuple(a)])
-print("cases %d, on the sliding correlation kernel %d, mismatches %d" % (n_cases, dense, bad))
+print("cases %d, on the sliding kernels %d, mismatches %d" % (n_cases, dense, bad))
 sys.exit(1 if bad else 0)

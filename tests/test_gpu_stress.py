@@ -20,7 +20,8 @@ def test_dense_kernel_random_configs(seed):
 
 @pytest.mark.parametrize("seed", [11])
 def test_dense_correlation_kernel_random_configs(seed):
-    """NCC / ZNCC, gray and colour, on the sliding-window correlation kernel: indices, f64 scores and MatchValues bit-exact."""
+    """NCC / ZNCC / SSD (gray and colour) and colour SAD on the sliding-window correlation kernel: indices, costs, f64 scores and
+    MatchValues bit-exact."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "stress_corr.py"), "70", str(seed)], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "mismatches 0" in r.stdout and "kernel 70," in r.stdout
+    assert "mismatches 0" in r.stdout and "kernels 70," in r.stdout

@@ -272,7 +272,7 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
     }
     if (e != cudaErrorNotSupported) return fail(ctx, USV_ERR_CUDA, "dense launch: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
-    if (p->cost_kind == USV_COST_NCC || p->cost_kind == USV_COST_ZNCC || p->cost_kind == USV_COST_SSD) {
+    {
       // sliding-window correlation kernel: planes + window statistics live in a scratch buffer, pairs run in chunks
       const size_t per_pair = usv::corr_scratch_bytes_per_pair(J, nullptr);
       const size_t cap = (size_t)3 << 29;  // 1.5 GB

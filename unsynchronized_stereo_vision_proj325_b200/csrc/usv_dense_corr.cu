@@ -1,5 +1,7 @@
 // usv_dense_corr.cu — dense stride-1 sweep for the correlation costs (NCC, ZNCC), gray or interleaved colour:
 // the sliding-window formulation of usv_dense.cu with IDP.4A in place of VABSDIFF4 and an exact f64 score.
+// The same kernel also runs SSD (Saa + Sbb - 2 Sab from the same sums, carried as the exact f64 "score" -SSD) and SAD
+// on colour frames (VABSDIFF4 per plane, "score" = -SAD); see kOpCorr / kOpSsd / kOpSad.
 //
 //   cost(x, x') = 1 - score,   NCC : score = (Sab * ra) * rb,            ra = 1/sqrt(Saa), rb = 1/sqrt(Sbb)
 //                              ZNCC: score = ((n Sab - Sa Sb) * ra) * rb, ra = 1/sqrt(n Saa - Sa^2), rb likewise
@@ -36,6 +38,9 @@ constexpr int kCLW = 32;          // words per L copy row
 constexpr int kCRW = 44;          // words per R copy row (40 used)
 constexpr int kCRowWords = 4 * kCLW + 4 * kCRW;
 constexpr int kNoX = 0x7fffffff;  // x' of "no candidate yet"
+// inner operation / scoring: correlation (NCC, ZNCC), SSD = Saa + Sbb - 2 Sab from the same IDP.4A sums, or SAD with
+// VABSDIFF4 in place of IDP.4A (colour frames: the gray SAD sweep has its own integer-key kernel, usv_dense.cu)
+constexpr int kOpCorr = 0, kOpSsd = 1, kOpSad = 2;
 
 struct CorrCfg {
   const uint8_t* lp;   // planes of the left frames  [pair][plane][H][pitch]
@@ -61,11 +66,12 @@ __device__ __forceinline__ bool corr_better(double sc_o, int x_o, double sc_m, i
   return vo < vm || (vo == vm && x_o < x_m);
 }
 
-template <int DIR, int NW, int NPL, bool SSD>
+template <int DIR, int NW, int NPL, int OP>
 __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, uint32_t* s_ring, double* s_bsc, int* s_bx,
                                           const uint8_t* __restrict__ Lb, const uint8_t* __restrict__ Rb, const double2* __restrict__ stl,
                                           const double2* __restrict__ str, const int X0, const int XR0, const int dbase, const int y0,
                                           const int rows_in) {
+  constexpr bool SSD = OP != kOpCorr;  // integer costs: "score" = -cost, no normalisation
   const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;
   const int ul = lane & 3, dl = lane >> 2, q = dl & 3, jh = dl >> 2;
   const int th = J.th;
@@ -140,7 +146,10 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) V[i][j] = dp4a_u8(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t rw = Rw[DIR < 0 ? i - j + 4 : i + j];
+            V[i][j] = OP == kOpSad ? sad4_acc(Lw[i], rw, V[i][j]) : dp4a_u8(Lw[i], rw, V[i][j]);
+          }
       }
       if (HAS_OLD) {
         const uint4* lo = reinterpret_cast<const uint4*>(my_l + (size_t)((2 * kCRB + slot) * NPL + pl) * kCRowWords);
@@ -151,7 +160,10 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) V[i][j] -= dp4a_u8(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t rw = Rw[DIR < 0 ? i - j + 4 : i + j];
+            V[i][j] -= OP == kOpSad ? sad4_acc(Lw[i], rw, 0u) : dp4a_u8(Lw[i], rw, 0u);
+          }
       }
     }
     if (HAS_KEYS) {
@@ -251,7 +263,7 @@ __device__ __forceinline__ void corr_pass(const DevJob& J, const CorrCfg& cfg, u
   }
 }
 
-template <int DIR, int NW, int NPL, bool SSD>
+template <int DIR, int NW, int NPL, int OP>
 __global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const DevJob J, const CorrCfg cfg) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* s_ring = smem_u32;                                              // [2][2*kCRB][NPL][kCRowWords]
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const D
     const int D0 = d_lo + 32 * pass;
     const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
-    corr_pass<DIR, NW, NPL, SSD>(J, cfg, s_ring, s_bsc, s_bx, Lb, Rb, stl, str, X0, XR0, dbase, y0, rows_in);
+    corr_pass<DIR, NW, NPL, OP>(J, cfg, s_ring, s_bsc, s_bx, Lb, Rb, stl, str, X0, XR0, dbase, y0, rows_in);
   }
   __syncthreads();
 
@@ -300,9 +312,9 @@ __global__ void __launch_bounds__(kCThreads, 3) dense_corr_argmin_kernel(const D
     const long long w = (long long)y * J.nx + x;
     const long long g = (long long)(cfg.pair0 + pair) * J.n_templates + w;
     if (xr == kNoX) write_result(J, g, (uint32_t)w, x, y, -1, 0xffffffffu, 0.0, __longlong_as_double(0x7ff0000000000000ll));
-    else if (SSD) {
+    else if (OP != kOpCorr) {
       const uint32_t raw = (uint32_t)(-sc);
-      write_result(J, g, (uint32_t)w, x, y, xr, raw, 0.0, normalised_cost(raw, USV_COST_SSD, J.n_elems));
+      write_result(J, g, (uint32_t)w, x, y, xr, raw, 0.0, normalised_cost(raw, OP == kOpSad ? USV_COST_SAD : USV_COST_SSD, J.n_elems));
     } else write_result(J, g, (uint32_t)w, x, y, xr, 0xffffffffu, __dadd_rn(sc, 0.0), __dsub_rn(1.0, sc));  // -0.0 -> 0.0 (flat windows)
   }
 }
@@ -359,7 +371,10 @@ __global__ void corr_stats_kernel(const uint2* __restrict__ rs, int height, int 
     const uint2 qin = __ldg(col + (long long)(y + th - 1) * nxc);
     sa += qin.x; saa += qin.y;
     double m, r;
-    if (kind == USV_COST_SSD) {
+    if (kind == USV_COST_SAD) {
+      m = 0.0;  // score = -SAD
+      r = 1.0;
+    } else if (kind == USV_COST_SSD) {
       m = -(double)saa;  // both cameras: score = 2 Sab - Saa - Sbb
       r = 1.0;
     } else if (kind == USV_COST_NCC) {
@@ -388,7 +403,8 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
                               int* n_launches) {
   *n_launches = 0;
   if (J.tx || J.sx != 1 || J.sy != 1) return cudaErrorNotSupported;
-  if (J.cost_kind != USV_COST_NCC && J.cost_kind != USV_COST_ZNCC && J.cost_kind != USV_COST_SSD) return cudaErrorNotSupported;
+  if (J.cost_kind != USV_COST_NCC && J.cost_kind != USV_COST_ZNCC && J.cost_kind != USV_COST_SSD && J.cost_kind != USV_COST_SAD)
+    return cudaErrorNotSupported;
   if (J.channels != 1 && J.channels != 3) return cudaErrorNotSupported;
   const int nw = J.tw / 4;
   if (J.tw % 4 != 0 || !(nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) || J.th > 64) return cudaErrorNotSupported;
@@ -403,8 +419,8 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   cfg.stride_px = 4 * (32 - nw + 1);
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
   cfg.x_off = J.camera_side == USV_LEFT_CAM ? ((cfg.n_xtiles * cfg.stride_px - J.nxc) & ~3) : 0;
-  cfg.n_eff = J.cost_kind == USV_COST_ZNCC ? (double)J.n_elems : J.cost_kind == USV_COST_SSD ? 2.0 : 1.0;
-  const bool ssd = J.cost_kind == USV_COST_SSD;
+  cfg.n_eff = J.cost_kind == USV_COST_ZNCC ? (double)J.n_elems : J.cost_kind == USV_COST_SSD ? 2.0 : J.cost_kind == USV_COST_SAD ? -1.0 : 1.0;
+  const int op = J.cost_kind == USV_COST_SSD ? kOpSsd : J.cost_kind == USV_COST_SAD ? kOpSad : kOpCorr;
   const int npl = J.channels;
   const size_t ring_bytes = (size_t)4 * kCRB * npl * kCRowWords * 4;
   const size_t smem_budget = 74 * 1024;  // three CTAs per SM
@@ -456,7 +472,9 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     const dim3 grid(cfg.n_xtiles, cfg.n_bands, np), block(kCThreads);
 #define USV_CORR_LAUNCH(D, NWW, NPLL)                                                                      \
   {                                                                                                        \
-    auto kfn = ssd ? dense_corr_argmin_kernel<D, NWW, NPLL, true> : dense_corr_argmin_kernel<D, NWW, NPLL, false>; \
+    auto kfn = op == kOpSsd ? dense_corr_argmin_kernel<D, NWW, NPLL, kOpSsd>                               \
+             : op == kOpSad ? dense_corr_argmin_kernel<D, NWW, NPLL, kOpSad>                               \
+                            : dense_corr_argmin_kernel<D, NWW, NPLL, kOpCorr>;                             \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     if (e != cudaSuccess) return e;                                                                        \
     kfn<<<grid, block, smem, st>>>(J, cfg);                                                                \
