@@ -305,6 +305,23 @@ int usv_stream_submit(usv_stream *s, int32_t slot, int32_t n_pairs);
 int usv_stream_submit_from(usv_stream *s, int32_t slot, const uint8_t *h_left,
                            const uint8_t *h_right,
                            const usv_frame_desc *host_frame, int32_t n_pairs);
+/* Same, for unsynchronised streams (P/Main.cpp:876-905 keeps three frames per
+ * camera; here the cameras write into frame stores): pair k of the slot is
+ * left_store[idx_left[k]] with right_store[idx_right[k]], frames laid out per
+ * `store_frame` (frame_stride = bytes between store frames), n_store_frames
+ * per store. Frames go store -> HBM directly (one copy per run of consecutive
+ * indices); register the stores with usv_host_register for asynchronous
+ * copies. */
+int usv_stream_submit_gather(usv_stream *s, int32_t slot,
+                             const uint8_t *left_store, const int32_t *idx_left,
+                             const uint8_t *right_store,
+                             const int32_t *idx_right, int64_t n_store_frames,
+                             const usv_frame_desc *store_frame,
+                             int32_t n_pairs);
+/* Page-lock / release a caller-owned host buffer (frame store, result array)
+ * so that copies from / to it overlap with the kernels. */
+int usv_host_register(usv_ctx *ctx, void *p, size_t bytes);
+int usv_host_unregister(usv_ctx *ctx, void *p);
 /* Block until the slot's D2H has landed. */
 int usv_stream_wait(usv_stream *s, int32_t slot);
 /* Bytes moved per submitted pair (for the bench's e2e accounting). */

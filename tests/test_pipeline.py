@@ -42,6 +42,13 @@ class StubStream:
         s["out"]["raw_cost"][:n, 1] = s["right"][:n].reshape(n, -1).sum(1)
         s["out"]["disparity_u16"][:n, 0] = s["left"][:n, 0, 0]
 
+    def submit_gather(self, slot, left_store, idx_left, right_store, idx_right):
+        n = len(idx_left)
+        s = self.slots[slot]
+        s["left"][:n] = left_store[idx_left].reshape(n, s["left"].shape[1], -1)
+        s["right"][:n] = right_store[idx_right].reshape(n, s["right"].shape[1], -1)
+        self.submit(slot, n)
+
     def wait(self, slot):
         self.in_flight.discard(slot)
 
@@ -95,6 +102,37 @@ def test_two_rank_gloo_matches_single_rank():
     rc = np.array(merged["raw_cost"])
     assert np.array_equal(rc[:, 0], fl[li].reshape(len(li), -1).sum(1)) and np.array_equal(rc[:, 1], fr[ri].reshape(len(ri), -1).sum(1))
     assert len(li) > 40 and (np.abs(np.array(merged["dt"])) <= 1 / 60).all()
+
+
+def test_gather_mode_equals_staged_mode():
+    fl, tl, fr, tr = _streams()
+    p = _abi.make_params(tmpl_w=4, tmpl_h=4)
+    a = pipeline.match_streams(fl, tl, fr, tr, p, pairs_per_slot=4, n_slots=3, stream_factory=StubStream)
+    b = pipeline.match_streams(fl, tl, fr, tr, p, pairs_per_slot=4, n_slots=3, stream_factory=StubStream, gather=True)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w", [128, 150])
+def test_streams_gather_on_gpu_vs_oracle(oracle, w):
+    """Frames go from the cameras' (page-locked) frame stores straight to HBM: same results as the staged ring, both for
+    a store pitch equal to the device pitch (one copy per run of consecutive frames) and for one that needs 2-D copies."""
+    n, h = 40, 40
+    left, right = synth.make_pairs(n, w, h, 1, shift=9, noise_sigma=2.0, seed=4)
+    tl, idl = synth.make_timestamps(n, drop_prob=0.1, seed=1)
+    tr, idr = synth.make_timestamps(n, phase=0.011, drop_prob=0.1, seed=2)
+    fl, fr = np.ascontiguousarray(left[idl]), np.ascontiguousarray(right[idr])
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad", search_max=31)
+    ctx = api.Context(0)
+    res = pipeline.match_streams(fl, tl, fr, tr, p, ctx=ctx, pairs_per_slot=8, n_slots=3, gather=True)
+    li, ri = res["pair_left"], res["pair_right"]
+    exp = oracle.match_dense(fl[li], fr[ri], p, mask=_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST)
+    assert np.array_equal(res["raw_cost"], exp["raw_cost"]) and np.array_equal(res["disparity_u16"], exp["disparity_u16"])
+    st = ctx.stream(_abi.frame_desc_for(fl), p, pairs_per_slot=4, n_slots=1)
+    with pytest.raises(api.UsvError):
+        st.submit_gather(0, fl, [0, len(fl)], fr, [0, 1])  # index outside the store
+    st.close()
+    ctx.close()
 
 
 @pytest.mark.gpu

@@ -21,7 +21,8 @@ EXPORTS = (
     "usv_grid_dims", "usv_match_dense_device", "usv_match_dense_host", "usv_match_templates_device",
     "usv_match_templates_host", "usv_disparity_to_distance", "usv_moving_object_distance",
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
-    "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_wait",
+    "usv_stream_slot", "usv_stream_frame_desc", "usv_stream_submit", "usv_stream_submit_from", "usv_stream_submit_gather",
+    "usv_stream_wait", "usv_host_register", "usv_host_unregister",
     "usv_stream_bytes_per_pair", "usv_probe_issue_rate", "usv_match_contours",
     "usv_resolve_match_list", "usv_resolve_match_list_device", "usv_id_matcher", "usv_preprocess_device", "usv_preprocess_host",
 )
@@ -288,6 +289,13 @@ class Context:
         self._check(lib().usv_probe_issue_rate(self._h, C.c_int32(which), C.c_double(target_ms), C.byref(r)), "usv_probe_issue_rate")
         return r.value
 
+    def host_register(self, array):
+        """Page-lock a caller-owned numpy array (a frame store) so that copies from it are asynchronous."""
+        self._check(lib().usv_host_register(self._h, _ptr(array), C.c_size_t(array.nbytes)), "usv_host_register")
+
+    def host_unregister(self, array):
+        self._check(lib().usv_host_unregister(self._h, _ptr(array)), "usv_host_unregister")
+
     def stream(self, frame, params, pairs_per_slot, n_slots=3, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST):
         return Stream(self, frame, params, pairs_per_slot, n_slots, mask)
 
@@ -341,6 +349,18 @@ class Stream:
         n = left.shape[0] if n_pairs is None else n_pairs
         self.ctx._check(lib().usv_stream_submit_from(self._h, C.c_int32(slot), _ptr(left), _ptr(right), C.byref(f), C.c_int32(n)),
                         "usv_stream_submit_from")
+
+    def submit_gather(self, slot, left_store, idx_left, right_store, idx_right):
+        """Enqueue pairs (left_store[idx_left[k]], right_store[idx_right[k]]) straight from two host frame stores
+        [n, H, W(, C)] (register them with Context.host_register for asynchronous copies): no staging memcpy on the host."""
+        f = _abi.frame_desc_for(left_store)
+        il = np.ascontiguousarray(idx_left, np.int32)
+        ir = np.ascontiguousarray(idx_right, np.int32)
+        if len(il) != len(ir) or left_store.shape != right_store.shape:
+            raise ValueError("index lists / frame stores differ in shape")
+        self.ctx._check(lib().usv_stream_submit_gather(self._h, C.c_int32(slot), _ptr(left_store), _ptr(il), _ptr(right_store), _ptr(ir),
+                                                       C.c_int64(left_store.shape[0]), C.byref(f), C.c_int32(len(il))),
+                        "usv_stream_submit_gather")
 
     def wait(self, slot):
         self.ctx._check(lib().usv_stream_wait(self._h, C.c_int32(slot)), "usv_stream_wait")

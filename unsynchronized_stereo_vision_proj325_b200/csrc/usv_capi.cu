@@ -826,16 +826,10 @@ extern "C" int usv_stream_frame_desc(const usv_stream* s, usv_frame_desc* out) {
   return USV_OK;
 }
 
-extern "C" int usv_stream_submit(usv_stream* s, int32_t slot, int32_t n_pairs) {
-  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+// kernels + D2H + completion event of a slot whose frames are already enqueued on its stream
+static int enqueue_match_and_results(usv_stream* s, Slot& sl, int32_t n_pairs) {
   usv_ctx* ctx = s->ctx;
-  if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
-  CU(cudaSetDevice(ctx->device));
-  Slot& sl = s->slots[slot];
   if (n_pairs > 0) {
-    const size_t fbytes = (size_t)s->hf.frame_stride * n_pairs;
-    CU(cudaMemcpyAsync(sl.d_l, sl.h_l, fbytes, cudaMemcpyHostToDevice, sl.st));
-    CU(cudaMemcpyAsync(sl.d_r, sl.h_r, fbytes, cudaMemcpyHostToDevice, sl.st));
     int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
     if (rc) return rc;
     const size_t n_res = (size_t)s->n_win * n_pairs;
@@ -847,41 +841,103 @@ extern "C" int usv_stream_submit(usv_stream* s, int32_t slot, int32_t n_pairs) {
   return USV_OK;
 }
 
+static int check_host_frame(usv_stream* s, const usv_frame_desc* hf) {
+  if (hf->width != s->hf.width || hf->height != s->hf.height || hf->channels != s->hf.channels ||
+      hf->row_stride < hf->width * hf->channels)
+    return fail(s->ctx, USV_ERR_INVALID_ARG, "frame geometry differs from the stream's");
+  return USV_OK;
+}
+
+// H2D of `n` consecutive host frames (layout `hf`) into consecutive device frames starting at `dst`
+static int enqueue_frames(usv_stream* s, Slot& sl, uint8_t* dst, const uint8_t* src, const usv_frame_desc* hf, int32_t n) {
+  usv_ctx* ctx = s->ctx;
+  const int row_bytes = hf->width * hf->channels;
+  if (hf->row_stride == s->df.row_stride && (n == 1 || hf->frame_stride == s->df.frame_stride)) {
+    const size_t bytes = n == 1 ? (size_t)hf->row_stride * hf->height : (size_t)s->df.frame_stride * n;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sl.st));
+  } else if (n == 1 || hf->frame_stride == (int64_t)hf->row_stride * hf->height) {
+    CU(cudaMemcpy2DAsync(dst, s->df.row_stride, src, hf->row_stride, row_bytes, (size_t)hf->height * n, cudaMemcpyHostToDevice, sl.st));
+  } else {
+    for (int i = 0; i < n; ++i)
+      CU(cudaMemcpy2DAsync(dst + (size_t)i * s->df.frame_stride, s->df.row_stride, src + (size_t)i * hf->frame_stride, hf->row_stride,
+                           row_bytes, hf->height, cudaMemcpyHostToDevice, sl.st));
+  }
+  return USV_OK;
+}
+
+extern "C" int usv_stream_submit(usv_stream* s, int32_t slot, int32_t n_pairs) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  usv_ctx* ctx = s->ctx;
+  if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
+  CU(cudaSetDevice(ctx->device));
+  Slot& sl = s->slots[slot];
+  if (n_pairs > 0) {
+    const size_t fbytes = (size_t)s->hf.frame_stride * n_pairs;
+    CU(cudaMemcpyAsync(sl.d_l, sl.h_l, fbytes, cudaMemcpyHostToDevice, sl.st));
+    CU(cudaMemcpyAsync(sl.d_r, sl.h_r, fbytes, cudaMemcpyHostToDevice, sl.st));
+  }
+  return enqueue_match_and_results(s, sl, n_pairs);
+}
+
 extern "C" int usv_stream_submit_from(usv_stream* s, int32_t slot, const uint8_t* h_left, const uint8_t* h_right,
                                       const usv_frame_desc* hf, int32_t n_pairs) {
   if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
   usv_ctx* ctx = s->ctx;
   if (!h_left || !h_right || !hf) return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
   if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
-  if (hf->width != s->hf.width || hf->height != s->hf.height || hf->channels != s->hf.channels ||
-      hf->row_stride < hf->width * hf->channels)
-    return fail(ctx, USV_ERR_INVALID_ARG, "frame geometry differs from the stream's");
+  int rc = check_host_frame(s, hf);
+  if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
   Slot& sl = s->slots[slot];
   if (n_pairs > 0) {
-    const int row_bytes = hf->width * hf->channels;
-    const uint8_t* src[2] = {h_left, h_right};
-    uint8_t* dst[2] = {sl.d_l, sl.d_r};
-    for (int k = 0; k < 2; ++k) {
-      if (hf->row_stride == s->df.row_stride && hf->frame_stride == s->df.frame_stride) {
-        CU(cudaMemcpyAsync(dst[k], src[k], (size_t)s->df.frame_stride * n_pairs, cudaMemcpyHostToDevice, sl.st));
-      } else if (n_pairs == 1 || hf->frame_stride == (int64_t)hf->row_stride * hf->height) {
-        CU(cudaMemcpy2DAsync(dst[k], s->df.row_stride, src[k], hf->row_stride, row_bytes, (size_t)hf->height * n_pairs,
-                             cudaMemcpyHostToDevice, sl.st));
-      } else {
-        for (int i = 0; i < n_pairs; ++i)
-          CU(cudaMemcpy2DAsync(dst[k] + (size_t)i * s->df.frame_stride, s->df.row_stride, src[k] + (size_t)i * hf->frame_stride,
-                               hf->row_stride, row_bytes, hf->height, cudaMemcpyHostToDevice, sl.st));
-      }
-    }
-    int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
-    if (rc) return rc;
-    const size_t n_res = (size_t)s->n_win * n_pairs;
-    for (int i = 0; i < kNumOut; ++i)
-      if (*out_slot(&sl.h_out, i))
-        CU(cudaMemcpyAsync(*out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res, cudaMemcpyDeviceToHost, sl.st));
+    if ((rc = enqueue_frames(s, sl, sl.d_l, h_left, hf, n_pairs))) return rc;
+    if ((rc = enqueue_frames(s, sl, sl.d_r, h_right, hf, n_pairs))) return rc;
   }
-  CU(cudaEventRecord(sl.done, sl.st));
+  return enqueue_match_and_results(s, sl, n_pairs);
+}
+
+extern "C" int usv_stream_submit_gather(usv_stream* s, int32_t slot, const uint8_t* left_store, const int32_t* idx_left,
+                                        const uint8_t* right_store, const int32_t* idx_right, int64_t n_store_frames,
+                                        const usv_frame_desc* hf, int32_t n_pairs) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  usv_ctx* ctx = s->ctx;
+  if (!left_store || !right_store || !idx_left || !idx_right || !hf) return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
+  if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
+  int rc = check_host_frame(s, hf);
+  if (rc) return rc;
+  for (int i = 0; i < n_pairs; ++i)
+    if (idx_left[i] < 0 || idx_left[i] >= n_store_frames || idx_right[i] < 0 || idx_right[i] >= n_store_frames)
+      return fail(ctx, USV_ERR_INVALID_ARG, "pair %d: frame index outside the store", i);
+  CU(cudaSetDevice(ctx->device));
+  Slot& sl = s->slots[slot];
+  const uint8_t* store[2] = {left_store, right_store};
+  const int32_t* idx[2] = {idx_left, idx_right};
+  uint8_t* dst[2] = {sl.d_l, sl.d_r};
+  for (int k = 0; k < 2; ++k) {
+    // runs of consecutive store frames travel as one copy (paired unsynchronised streams are mostly consecutive)
+    for (int i = 0; i < n_pairs;) {
+      int j = i + 1;
+      while (j < n_pairs && idx[k][j] == idx[k][j - 1] + 1) ++j;
+      if ((rc = enqueue_frames(s, sl, dst[k] + (size_t)i * s->df.frame_stride, store[k] + (size_t)idx[k][i] * hf->frame_stride, hf, j - i)))
+        return rc;
+      i = j;
+    }
+  }
+  return enqueue_match_and_results(s, sl, n_pairs);
+}
+
+extern "C" int usv_host_register(usv_ctx* ctx, void* p, size_t bytes) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (!p || bytes == 0) return fail(ctx, USV_ERR_INVALID_ARG, "null buffer");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return USV_OK;
+}
+
+extern "C" int usv_host_unregister(usv_ctx* ctx, void* p) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (!p) return fail(ctx, USV_ERR_INVALID_ARG, "null buffer");
+  CU(cudaHostUnregister(p));
   return USV_OK;
 }
 

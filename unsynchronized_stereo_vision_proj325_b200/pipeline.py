@@ -32,13 +32,15 @@ def default_matcher(ctx, frame, params, pairs_per_slot, n_slots, mask):
 
 def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0 / 60.0, rank=0, world=1, ctx=None,
                   pairs_per_slot=16, n_slots=3, mask=_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST, stream_factory=default_matcher,
-                  copy_threads=1):
+                  copy_threads=1, gather=False):
     """Pair two unsynchronised streams and match this rank's shard of the pairs.
 
     frames_*: [n, H, W(, C)] uint8 arrays (host) indexed by frame number; t_*: ascending timestamps.
     Returns dict(pair_left, pair_right, dt — for this rank's pairs — and one array per output in `mask`).
     `stream_factory(ctx, frame, params, pairs_per_slot, n_slots, mask)` must return an object with the
     usv_stream interface (slots / submit / wait / close); tests inject a CPU stub to exercise the host logic.
+    gather=True: frames_* are the cameras' frame stores and the paired frames go store -> HBM directly
+    (usv_stream_submit_gather; the stores are page-locked for the duration of the call) — no staging memcpy on the host.
     """
     li, ri, dt = pair_streams(t_left, t_right, max_dt)
     lo, hi = shard_range(len(li), rank, world)
@@ -51,7 +53,16 @@ def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0
     outs = {name: [] for name, bit, _ in _abi.OUTPUT_FIELDS if mask & bit}
     pending = []  # (slot, count) in submission order
     pool = None
-    if copy_threads > 1:  # the "capture" memcpy into the pinned ring is the host-side bound of the stream: spread it
+    registered = []
+    if gather and ctx is not None:
+        for store in (frames_left, frames_right):
+            if store.flags["C_CONTIGUOUS"] and store.nbytes:
+                try:
+                    ctx.host_register(store)
+                    registered.append(store)
+                except api.UsvError:
+                    pass  # already page-locked by the caller (or not lockable): the copies still work, synchronously
+    if copy_threads > 1 and not gather:  # the "capture" memcpy into the pinned ring is the host-side bound of the stream: spread it
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(copy_threads)
 
@@ -66,6 +77,10 @@ def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0
         if len(pending) == n_slots:
             drain_one()  # the oldest in-flight batch owns this slot
         cnt = min(pairs_per_slot, n - b0)
+        if gather:
+            st.submit_gather(slot, frames_left, li[b0:b0 + cnt], frames_right, ri[b0:b0 + cnt])
+            pending.append((slot, cnt))
+            continue
         # "capture": the paired frames land in the slot's pinned buffers
         sl, sr = st.slots[slot]["left"], st.slots[slot]["right"]
         if pool is None:
@@ -79,6 +94,8 @@ def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0
     while pending:
         drain_one()
     st.close()
+    for store in registered:
+        ctx.host_unregister(store)
     if pool is not None:
         pool.shutdown()
     res = {"pair_left": li, "pair_right": ri, "dt": dt}
