@@ -120,6 +120,12 @@ typedef struct usv_outputs {
                               bits (else USV_ERR_UNSUPPORTED); lossless        */
 } usv_outputs;
 
+/* A context owns grow-only device scratch (staging buffers, distance LUTs,
+ * the workspaces of the correlation / resolve / pre-pass kernels), so calls
+ * on ONE context must not overlap: one host thread at a time, and *_device
+ * calls enqueued on different CUDA streams must be ordered by the caller.
+ * For overlapped execution use a usv_stream (every slot owns its stream and
+ * its scratch) or one context per stream; contexts are cheap. */
 typedef struct usv_ctx usv_ctx;       /* one per (GPU, host thread)          */
 typedef struct usv_stream usv_stream; /* pinned ring + CUDA streams          */
 

@@ -234,6 +234,30 @@ def test_stream_matches_oracle(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cost,c", [("zncc", 3), ("ssd", 1)])
+def test_stream_slots_do_not_share_scratch(ctx, oracle, cost, c):
+    """The sliding correlation kernel keeps planes and window statistics in a scratch buffer; slots of a stream run
+    concurrently on their own CUDA streams and must each own one (several batches in flight, then compare)."""
+    w, h, n_slots, pps = 200, 60, 4, 2
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost=cost, search_max=63)
+    left, right = synth.make_pairs(n_slots * pps * 2, w, h, c, shift=11, noise_sigma=2.0, seed=21)
+    exp = oracle.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX)
+    st = ctx.stream(_abi.frame_desc_for(left), p, pairs_per_slot=pps, n_slots=n_slots, mask=_abi.OUT_RIGHT_INDEX)
+    for rnd in range(2):
+        for s in range(n_slots):
+            a = (rnd * n_slots + s) * pps
+            st.slots[s]["left"][:] = left[a:a + pps].reshape(pps, h, w * c)
+            st.slots[s]["right"][:] = right[a:a + pps].reshape(pps, h, w * c)
+            st.submit(s)
+        assert ctx.last_kernel == "dense_corr_argmin_kernel"
+        for s in range(n_slots):
+            st.wait(s)
+            a = (rnd * n_slots + s) * pps
+            assert np.array_equal(st.slots[s]["out"]["right_index"], exp["right_index"][a:a + pps]), (rnd, s)
+    st.close()
+
+
+@pytest.mark.gpu
 def test_raw_cost_u16_is_lossless_or_refused(ctx, oracle):
     """raw_cost_u16 (include/usv_b200.h): same costs as raw_cost for templates whose SAD fits 16 bits, 0xFFFF for
     windows without candidates, USV_ERR_UNSUPPORTED otherwise."""

@@ -238,7 +238,7 @@ extern "C" int usv_grid_dims(const usv_frame_desc* f, const usv_search_params* p
 // ---- matching: device pointers -----------------------------------------------------
 static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, const usv_frame_desc* f, int32_t n_pairs,
                         const usv_search_params* p, const usv_outputs* d_out, const int32_t* d_tx, const int32_t* d_ty,
-                        int32_t n_templates, uint32_t* d_cost_rows, double* d_score_rows, int32_t row_cap, cudaStream_t st) {
+                        int32_t n_templates, uint32_t* d_cost_rows, double* d_score_rows, int32_t row_cap, cudaStream_t st, DevBuf* corr_ws = nullptr) {
   int rc = check_common(ctx, f, p, n_pairs);
   if (rc) return rc;
   if (!d_left || !d_right || !d_out) return fail(ctx, USV_ERR_INVALID_ARG, "null device pointer");
@@ -278,8 +278,10 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
       const size_t cap = (size_t)3 << 29;  // 1.5 GB
       size_t want = per_pair * (size_t)n_pairs;
       if (want > cap) want = std::max(per_pair, cap / per_pair * per_pair);
-      if ((rc = grow(ctx, ctx->corr_ws, want))) return rc;
-      e = usv::launch_dense_corr(J, n_pairs, ctx->corr_ws.p, ctx->corr_ws.cap, st, &name, &nl);
+      // the scratch belongs to whoever owns the stream: launches on different streams must not share it
+      DevBuf& ws = corr_ws ? *corr_ws : ctx->corr_ws;
+      if ((rc = grow(ctx, ws, want))) return rc;
+      e = usv::launch_dense_corr(J, n_pairs, ws.p, ws.cap, st, &name, &nl);
       if (e == cudaSuccess) {
         ctx->launches += nl;
         ctx->last_kernel = name;
@@ -729,6 +731,7 @@ struct Slot {
   cudaEvent_t done = nullptr;
   uint8_t *h_l = nullptr, *h_r = nullptr, *d_l = nullptr, *d_r = nullptr;
   usv_outputs h_out, d_out;
+  DevBuf corr_ws;  // planes + window statistics of the sliding correlation kernel: per slot, the slots run concurrently
 };
 
 struct usv_stream {
@@ -750,6 +753,7 @@ extern "C" int usv_stream_destroy(usv_stream* s) {
     if (sl.h_r) cudaFreeHost(sl.h_r);
     if (sl.d_l) cudaFree(sl.d_l);
     if (sl.d_r) cudaFree(sl.d_r);
+    if (sl.corr_ws.p) cudaFree(sl.corr_ws.p);
     for (int i = 0; i < kNumOut; ++i) {
       if (*out_slot(&sl.h_out, i)) cudaFreeHost(*out_slot(&sl.h_out, i));
       if (*out_slot(&sl.d_out, i)) cudaFree(*out_slot(&sl.d_out, i));
@@ -830,7 +834,8 @@ extern "C" int usv_stream_frame_desc(const usv_stream* s, usv_frame_desc* out) {
 static int enqueue_match_and_results(usv_stream* s, Slot& sl, int32_t n_pairs) {
   usv_ctx* ctx = s->ctx;
   if (n_pairs > 0) {
-    int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st);
+    int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st,
+                          &sl.corr_ws);
     if (rc) return rc;
     const size_t n_res = (size_t)s->n_win * n_pairs;
     for (int i = 0; i < kNumOut; ++i)
