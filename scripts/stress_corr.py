@@ -8,13 +8,15 @@ from oracle import oracle
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+mma_only = len(sys.argv) > 3 and sys.argv[3] == "mma"  # only the tensor-pipe kernel's coverage: 16 / 32-px templates, no SAD, wider frames
 ctx = api.Context(0)
 bad = dense = 0
+kernels = {}
 for t in range(n_cases):
-    tw = int(rng.choice([8, 12, 16, 24, 32]))
+    tw = int(rng.choice([16, 32] if mma_only else [8, 12, 16, 24, 32]))
     th = int(rng.choice([1, 4, 8, 13, 16, 24, 32]))
     c = int(rng.choice([1, 3]))
-    w = int(rng.integers(tw, 200))
+    w = int(rng.integers(tw, 700 if mma_only and rng.random() < 0.3 else 200))
     h = int(rng.integers(th, th + 40))
     n = int(rng.integers(1, 3))
     side = int(rng.integers(0, 2))
@@ -28,10 +30,11 @@ for t in range(n_cases):
         left[:] = 90; right[:] = 90                      # flat: zero variance everywhere (score 0, all ties)
     elif mode < 0.25:
         left[:, : h // 2] = 200; right[:, :, : w // 2] = 17   # flat regions next to texture
-    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=str(rng.choice(["ncc", "zncc", "ssd", "sad"])), search_min=lo, search_max=hi, camera_side=side,
+    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=str(rng.choice(["ncc", "zncc", "ssd"] if mma_only else ["ncc", "zncc", "ssd", "sad"])), search_min=lo, search_max=hi, camera_side=side,
                          accept_threshold=thr, distance_kind=int(rng.integers(0, 3)))
     got = ctx.match_dense(left, right, p)
-    dense += ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_sad_argmin_kernel")  # gray SAD has its own kernel
+    dense += ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_corr_mma_kernel", "dense_sad_argmin_kernel")  # gray SAD has its own kernel
+    kernels[ctx.last_kernel] = kernels.get(ctx.last_kernel, 0) + 1
     exp = oracle.match_dense(left, right, p)
     ok = all(np.array_equal(got[k], exp[k]) for k in ("right_index", "raw_cost", "disparity_u16"))
     ok = ok and got["matches"].tobytes() == exp["matches"].tobytes() and got["score"].tobytes() == exp["score"].tobytes()
@@ -45,5 +48,5 @@ for t in range(n_cases):
             ii = np.argwhere(got["right_index"] != exp["right_index"])[:4]
             for a in ii:
                 print("   win", a.tolist(), "got", got["right_index"][tuple(a)], got["score"][tuple(a)], "exp", exp["right_index"][tuple(a)], exp["score"][tuple(a)])
-print("cases %d, on the sliding kernels %d, mismatches %d" % (n_cases, dense, bad))
+print("cases %d, on the sliding kernels %d, mismatches %d, kernels %s" % (n_cases, dense, bad, kernels))
 sys.exit(1 if bad else 0)

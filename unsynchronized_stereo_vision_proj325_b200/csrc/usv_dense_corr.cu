@@ -27,8 +27,9 @@
 // statistics of the row (8 windows, 11 positions) sit in registers, and the running best per window is the pair
 // (score, x') in shared memory.
 #include <algorithm>
+#include <cstdlib>
 
-#include "usv_common.cuh"
+#include "usv_corr.cuh"
 
 namespace usv {
 
@@ -37,33 +38,10 @@ constexpr int kCRB = 2;           // rows per staging block (rows are long here:
 constexpr int kCLW = 32;          // words per L copy row
 constexpr int kCRW = 44;          // words per R copy row (40 used)
 constexpr int kCRowWords = 4 * kCLW + 4 * kCRW;
-constexpr int kNoX = 0x7fffffff;  // x' of "no candidate yet"
-// inner operation / scoring: correlation (NCC, ZNCC), SSD = Saa + Sbb - 2 Sab from the same IDP.4A sums, or SAD with
-// VABSDIFF4 in place of IDP.4A (colour frames: the gray SAD sweep has its own integer-key kernel, usv_dense.cu)
-constexpr int kOpCorr = 0, kOpSsd = 1, kOpSad = 2;
-
-struct CorrCfg {
-  const uint8_t* lp;   // planes of the left frames  [pair][plane][H][pitch]
-  const uint8_t* rp;
-  long long pair_stride, plane_stride;
-  int pitch;           // bytes between plane rows (multiple of 4)
-  const double2* stat_l;  // [pair][nyc][nxc] (-Sa, ra)
-  const double2* stat_r;  // [pair][nyc][nxc] ( Sb, rb)
-  double n_eff;        // n (ZNCC) or 1 (NCC)
-  int stride_px, n_xtiles, bh, n_bands, x_off;
-  int pair0;           // first pair of this launch inside the caller's batch (outputs are indexed by the global pair)
-};
-
 __device__ __forceinline__ uint32_t dp4a_u8(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
   asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
-}
-
-// (score, x') order of the reference: smaller cost v = 1 - score first, then smaller x' (P/Main.cpp:451)
-__device__ __forceinline__ bool corr_better(double sc_o, int x_o, double sc_m, int x_m) {
-  const double vo = __dsub_rn(1.0, sc_o), vm = __dsub_rn(1.0, sc_m);
-  return vo < vm || (vo == vm && x_o < x_m);
 }
 
 template <int DIR, int NW, int NPL, int OP>
@@ -395,8 +373,11 @@ size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out) {
   const int pitch = ((J.width + 15) & ~15) + 16;
   if (pitch_out) *pitch_out = pitch;
   const size_t planes = J.channels > 1 ? 2ull * J.channels * J.height * pitch : 0;
-  return planes + 2ull * J.nyc * J.nxc * sizeof(double2) + (size_t)J.height * J.nxc * sizeof(uint2) + 512;
+  return planes + 2ull * J.nyc * J.nxc * sizeof(double2) + (size_t)J.height * J.nxc * sizeof(uint2) + 512 + corr_mma_best_bytes_per_pair(J);
 }
+
+// Measurement switch (USV_CORR_MMA=0 keeps every correlation sweep on the ALU kernel, for A/B timing); read once.
+static const bool g_corr_use_mma = [] { const char* e = getenv("USV_CORR_MMA"); return !(e && e[0] == '0'); }();
 
 // Returns cudaErrorNotSupported when the job is outside the kernel's coverage (the caller then runs the direct form).
 cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
@@ -432,6 +413,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = ring_bytes + (size_t)cfg.bh * 128 * 12;
 
+  bool used_mma = false;
   for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
     const int np = std::min(chunk, n_pairs - p0);
     uint8_t* base = (uint8_t*)d_scratch;
@@ -469,6 +451,21 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     }
     cfg.stat_l = st_l; cfg.stat_r = st_r;
     cfg.pair0 = p0;
+    {
+      // NCC / ZNCC / SSD with 16- or 32-px templates: the row products run on the integer tensor pipe (usv_dense_mma.cu)
+      uint8_t* bb = (uint8_t*)(rsum + (size_t)np * J.height * J.nxc);
+      bb = (uint8_t*)(((uintptr_t)bb + 255) & ~(uintptr_t)255);
+      cfg.best_sc = (double*)bb;
+      cfg.best_x = (int*)(cfg.best_sc + (size_t)np * J.nyc * J.nxc);
+      cudaError_t e = g_corr_use_mma ? launch_corr_mma(J, cfg, op, np, st) : cudaErrorNotSupported;
+      if (e == cudaSuccess) {
+        *n_launches += 1;
+        used_mma = true;
+        continue;
+      }
+      if (e != cudaErrorNotSupported) return e;
+      (void)cudaGetLastError();
+    }
     const dim3 grid(cfg.n_xtiles, cfg.n_bands, np), block(kCThreads);
 #define USV_CORR_LAUNCH(D, NWW, NPLL)                                                                      \
   {                                                                                                        \
@@ -495,7 +492,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  *kernel_name = "dense_corr_argmin_kernel";
+  *kernel_name = used_mma ? "dense_corr_mma_kernel" : "dense_corr_argmin_kernel";
   return cudaSuccess;
 }
 
