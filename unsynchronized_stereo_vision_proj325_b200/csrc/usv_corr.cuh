@@ -21,7 +21,8 @@ struct CorrCfg {
   int stride_px, n_xtiles, bh, n_bands, x_off;
   int pair0;           // first pair of this launch inside the caller's batch (outputs are indexed by the global pair)
   // tensor-pipe kernel only: running best between passes over the candidate columns, [pair][nyc][nxc]
-  double* best_sc;
+  double* best_v;   // v = 1 - score
+  double* best_sc;  // the score itself (only when the caller asked for it)
   int* best_x;
 };
 

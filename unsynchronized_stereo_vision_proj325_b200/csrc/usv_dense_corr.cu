@@ -455,7 +455,8 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
       // NCC / ZNCC / SSD with 16- or 32-px templates: the row products run on the integer tensor pipe (usv_dense_mma.cu)
       uint8_t* bb = (uint8_t*)(rsum + (size_t)np * J.height * J.nxc);
       bb = (uint8_t*)(((uintptr_t)bb + 255) & ~(uintptr_t)255);
-      cfg.best_sc = (double*)bb;
+      cfg.best_v = (double*)bb;
+      cfg.best_sc = cfg.best_v + (size_t)np * J.nyc * J.nxc;
       cfg.best_x = (int*)(cfg.best_sc + (size_t)np * J.nyc * J.nxc);
       cudaError_t e = g_corr_use_mma ? launch_corr_mma(J, cfg, op, np, st) : cudaErrorNotSupported;
       if (e == cudaSuccess) {
