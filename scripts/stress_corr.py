@@ -13,8 +13,8 @@ ctx = api.Context(0)
 bad = dense = 0
 kernels = {}
 for t in range(n_cases):
-    tw = int(rng.choice([16, 32] if mma_only else [8, 12, 16, 24, 32]))
-    th = int(rng.choice([1, 4, 8, 13, 16, 24, 32]))
+    tw = int(rng.choice([1, 5, 8, 9, 12, 16, 16, 17, 20, 24, 31, 32, 32] if mma_only else [8, 12, 16, 24, 32]))
+    th = int(rng.choice([1, 4, 8, 13, 16, 24, 32] + ([70] if mma_only else [])))
     c = int(rng.choice([1, 3]))
     w = int(rng.integers(tw, 700 if mma_only and rng.random() < 0.3 else 200))
     h = int(rng.integers(th, th + 40))

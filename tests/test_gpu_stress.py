@@ -25,3 +25,23 @@ def test_dense_correlation_kernel_random_configs(seed):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "stress_corr.py"), "70", str(seed)], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mismatches 0" in r.stdout and "kernels 70," in r.stdout
+
+
+@pytest.mark.parametrize("seed", [21])
+def test_tensor_pipe_correlation_kernel_random_configs(seed):
+    """NCC / ZNCC / SSD on the tensor-pipe kernel (usv_dense_mma.cu: IMMA row products, sliding accumulators): template widths
+    1..32 incl. odd ones, any height, gray and colour, frames wide enough for several passes over the candidate columns, both
+    camera sides, bounded / negative / unbounded ranges, flat frames. Bit-exact, every case, and every case on that kernel."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "stress_corr.py"), "70", str(seed), "mma"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatches 0" in r.stdout and "'dense_corr_mma_kernel': 70" in r.stdout
+
+
+def test_alu_correlation_kernel_still_matches():
+    """USV_CORR_MMA=0 keeps the correlation sweeps on the ALU kernel (the A/B switch of the measurements): still bit-exact."""
+    env = dict(os.environ, USV_CORR_MMA="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "stress_corr.py"), "40", "5"], cwd=ROOT, capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatches 0" in r.stdout and "dense_corr_mma_kernel" not in r.stdout

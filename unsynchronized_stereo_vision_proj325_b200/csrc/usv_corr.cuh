@@ -35,5 +35,6 @@ __device__ __forceinline__ bool corr_better(double sc_o, int x_o, double sc_m, i
 // usv_dense_mma.cu: cudaErrorNotSupported when the job is outside the tensor-pipe kernel's coverage
 cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaStream_t st);
 size_t corr_mma_best_bytes_per_pair(const DevJob& J);
+bool corr_mma_supported(const DevJob& J, int op);
 
 }  // namespace usv

@@ -388,9 +388,14 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     return cudaErrorNotSupported;
   if (J.channels != 1 && J.channels != 3) return cudaErrorNotSupported;
   const int nw = J.tw / 4;
-  if (J.tw % 4 != 0 || !(nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) || J.th > 64) return cudaErrorNotSupported;
   if (J.cost_rows || J.score_rows) return cudaErrorNotSupported;
-  if (255ll * 255 * J.n_elems >= (1ll << 32)) return cudaErrorNotSupported;  // Sab must fit the u32 accumulators
+  const int op = J.cost_kind == USV_COST_SSD ? kOpSsd : J.cost_kind == USV_COST_SAD ? kOpSad : kOpCorr;
+  // the two sweeps: ALU kernel (this file; widths 8 / 12 / 16 / 24 / 32, th <= 64) and tensor-pipe kernel
+  // (usv_dense_mma.cu; any width up to 32, any height, not SAD), which is preferred where both apply
+  const bool alu_ok = J.tw % 4 == 0 && (nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) && J.th <= 64 &&
+                      255ll * 255 * J.n_elems < (1ll << 32);  // Sab must fit the u32 accumulators
+  const bool mma_ok = g_corr_use_mma && corr_mma_supported(J, op);
+  if (!alu_ok && !mma_ok) return cudaErrorNotSupported;
   int pitch;
   const size_t per_pair = corr_scratch_bytes_per_pair(J, &pitch);
   const int chunk = (int)std::min<size_t>((size_t)n_pairs, std::max<size_t>(1, scratch_bytes / per_pair));
@@ -401,7 +406,6 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
   cfg.x_off = J.camera_side == USV_LEFT_CAM ? ((cfg.n_xtiles * cfg.stride_px - J.nxc) & ~3) : 0;
   cfg.n_eff = J.cost_kind == USV_COST_ZNCC ? (double)J.n_elems : J.cost_kind == USV_COST_SSD ? 2.0 : J.cost_kind == USV_COST_SAD ? -1.0 : 1.0;
-  const int op = J.cost_kind == USV_COST_SSD ? kOpSsd : J.cost_kind == USV_COST_SAD ? kOpSad : kOpCorr;
   const int npl = J.channels;
   const size_t ring_bytes = (size_t)4 * kCRB * npl * kCRowWords * 4;
   const size_t smem_budget = 74 * 1024;  // three CTAs per SM
@@ -458,13 +462,13 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
       cfg.best_v = (double*)bb;
       cfg.best_sc = cfg.best_v + (size_t)np * J.nyc * J.nxc;
       cfg.best_x = (int*)(cfg.best_sc + (size_t)np * J.nyc * J.nxc);
-      cudaError_t e = g_corr_use_mma ? launch_corr_mma(J, cfg, op, np, st) : cudaErrorNotSupported;
+      cudaError_t e = mma_ok ? launch_corr_mma(J, cfg, op, np, st) : cudaErrorNotSupported;
       if (e == cudaSuccess) {
         *n_launches += 1;
         used_mma = true;
         continue;
       }
-      if (e != cudaErrorNotSupported) return e;
+      if (e != cudaErrorNotSupported || !alu_ok) return e;
       (void)cudaGetLastError();
     }
     const dim3 grid(cfg.n_xtiles, cfg.n_bands, np), block(kCThreads);

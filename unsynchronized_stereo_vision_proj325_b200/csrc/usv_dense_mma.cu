@@ -6,7 +6,8 @@
 // recast as a dense contraction and ncu shows it beats the ALU path"). For one image row v of one colour plane
 //     G_v[x, x'] = sum_{c < tw} L[v][x + c] * R[v][x' + c]
 // is a product of two Toeplitz matrices, A[x][c] = L[v][x + c] (16 windows x tw bytes) and B[c][x'] = R[v][x' + c]
-// (tw bytes x 8 candidates): one mma.m16n8k32 (tw = 32) or m16n8k16 (tw = 16) per (16 windows, 8 candidates, plane).
+// (tw bytes x 8 candidates): one mma.m16n8k32 (tw <= 32) or m16n8k16 (tw <= 16) per (16 windows, 8 candidates, plane);
+// the bytes of A beyond a narrower template are zeroed.
 // A fragment register of either operand is four consecutive bytes of the row at an arbitrary byte offset, i.e. one
 // word of one of the four byte-shifted copies of the row that the ALU kernels already keep in shared memory — no
 // im2col is ever materialised. Sab(x, x', y) = sum over the th rows of the window and the planes of G_v is slid down
@@ -59,7 +60,7 @@ __device__ __forceinline__ void imma_k16(int (&c)[4], uint32_t a0, uint32_t a1, 
 // (v, x') order of the reference: smaller cost v = 1 - score first, then smaller x' (P/Main.cpp:451)
 __device__ __forceinline__ bool v_better(double v_o, int x_o, double v_m, int x_m) { return v_o < v_m || (v_o == v_m && x_o < x_m); }
 
-// TW = template width (16 or 32) = K of one product; WS: the caller asked for the f64 score of the winner (otherwise
+// TW = K of one product (16 or 32; the template is tw <= TW bytes wide); WS: the caller asked for the f64 score of the winner (otherwise
 // only v = 1 - score, the MatchValue, is tracked). The camera side is a run-time sign: LeftCam x' = x - d, RightCam x + d.
 template <int TW, int NPL, int OP, bool WS>
 __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJob J, const CorrCfg cfg) {
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
   // shared memory by cp.async (no registers): 288 right positions + 32 left windows.
   constexpr int kChunks = kMLChunks + kMRChunks;
   constexpr int kTasks = 2 * NPL * kChunks;
-  static_assert(kTasks <= kMThreads, "one staging task per thread");
+  static_assert(kTasks <= kMThreads - 96 && kPassCols == 3 * 96, "ring tasks on warps 0..4, statistics on warps 5..7");
   const bool t_on = tid < kTasks;
   const int t_half = tid / (NPL * kChunks), t_rem = tid - t_half * (NPL * kChunks);
   const int t_pl = t_rem / kChunks, t_c = t_rem - t_pl * kChunks;
@@ -124,23 +125,17 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
       for (int k = 0; k < 5; ++k) pw[k] = __ldg(t_row + t_idx[k]);
       t_row += row_words;
     }
-    if (r >= th - 1) {
+    if (r >= th - 1 && tid >= kMThreads - 96) {  // warps 5..7: warps 0..4 carry the ring tasks
       const long long ro = (long long)(y0 + r - (th - 1)) * nxc;
-      const int slot = r & 1;
+      const int slot = r & 1, i = tid - (kMThreads - 96);
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int col = tid + k * kMThreads;
-        if (col < kPassCols) {
-          const int xk = xcol0 + col;
-          // a candidate outside the frame loses every comparison: NaN statistics
-          if (xk > nxc - 1) s_rs[slot * kPassCols + col] = make_double2(nan, nan);
-          else cp_async16(&s_rs[slot * kPassCols + col], str + ro + xk);
-        }
+      for (int k = 0; k < 3; ++k) {
+        const int col = i + k * 96, xk = xcol0 + col;
+        // a candidate outside the frame loses every comparison: NaN statistics
+        if (xk > nxc - 1) s_rs[slot * kPassCols + col] = make_double2(nan, nan);
+        else cp_async16(&s_rs[slot * kPassCols + col], str + ro + xk);
       }
-      if (tid >= kMThreads - kMWin) {
-        const int i = tid - (kMThreads - kMWin);
-        cp_async16(&s_ls[slot * kMWin + i], stl + ro + min(xm + i, nxc - 1));
-      }
+      if (i < kMWin) cp_async16(&s_ls[slot * kMWin + i], stl + ro + min(xm + i, nxc - 1));
     }
     cp_async_commit();
   };
@@ -159,11 +154,14 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
   // fragment words of this thread inside a (slot, plane): operand byte = base + g + 4t (+8 for row g + 8, +16 for the
   // upper half of K): copy g & 3, word (g >> 2) + t + ...
   const int a_off = (g & 3) * kMLW + 4 * mi + (g >> 2) + t;
+  // templates narrower than K: the bytes of A beyond the template width are zeroed (k = 4t + i, + 16 for the upper words)
+  auto byte_mask = [](int n) { return n >= 4 ? 0xffffffffu : n <= 0 ? 0u : (1u << (8 * n)) - 1u; };
+  const uint32_t a_mask_lo = byte_mask(J.tw - 4 * t), a_mask_hi = byte_mask(J.tw - 16 - 4 * t);
   const int b_off = 4 * kMLW + (g & 3) * kMRW + 2 * kNTW * q + (g >> 2) + t;
 
   // one warp per row merges the four quarters' winners and writes the results (last pass) or the running best
   auto merge_row = [&](int r, int pass) {
-    if (w != (r & 7)) return;
+    if (w != 5 + r % 3) return;
     const int par = r & 1;
     const int x = xm + lane, yo = y0 + r - (th - 1);
     double v = s_mv[(par * 4 + 0) * kMWin + lane], sc = WS ? s_msc[(par * 4 + 0) * kMWin + lane] : 0.0;
@@ -199,12 +197,15 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
     // [c_lo, c_hi]: bit jg of any_g = some entry may be a candidate. Skipping is only an optimisation: the range test
     // on d and the NaN statistics of out-of-frame columns reject every entry of a skipped group.
     const int xa = xm + 16 * mi;
-    uint32_t any_g = 0u;
+    uint32_t any_g = 0u, full_g = 0u;  // full: every entry of the group has d in range, the test is skipped
 #pragma unroll
     for (int jg = 0; jg < kNTW / kNG; ++jg) {
       const int cb = wcol0 + 8 * kNG * jg, ce = cb + 8 * kNG - 1;
       const int d_lo = leftcam ? xa - ce : cb - xa - 15, d_hi = leftcam ? xa + 15 - cb : ce - xa;
-      if (c_hi >= c_lo && cb <= c_hi && ce >= c_lo && d_hi >= J.dmin && d_lo <= J.dmax && xa <= nxc - 1) any_g |= 1u << jg;
+      if (c_hi >= c_lo && cb <= c_hi && ce >= c_lo && d_hi >= J.dmin && d_lo <= J.dmax && xa <= nxc - 1) {
+        any_g |= 1u << jg;
+        if (d_lo >= J.dmin && d_hi <= J.dmax) full_g |= 1u << jg;
+      }
     }
     // d - dmin of the thread's entry (eh, tile 0, el 0); tile j, el move it by -/+ (8 j + el)
     int ub[2];
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
           const uint32_t* bp = ring + pl * kMRowWords + b_off;
           uint32_t a[4], b[NB];
 #pragma unroll
-          for (int k = 0; k < NA; ++k) a[k] = ap[2 * k];
+          for (int k = 0; k < NA; ++k) a[k] = ap[2 * k] & (k < 2 ? a_mask_lo : a_mask_hi);
 #pragma unroll
           for (int j = 0; j < NB; ++j) b[j] = bp[2 * j];
 #pragma unroll
@@ -309,16 +310,21 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
                 }
             }
             // ascending x': a later equal candidate never replaces (P/Main.cpp:451)
+            auto update = [&](auto masked_t) {
 #pragma unroll
-            for (int jj = 0; jj < kNG; ++jj)
+              for (int jj = 0; jj < kNG; ++jj)
 #pragma unroll
-              for (int eh = 0; eh < 2; ++eh)
+                for (int eh = 0; eh < 2; ++eh)
 #pragma unroll
-                for (int el = 0; el < 2; ++el) {
-                  const int idx = 8 * (kNG * jg + jj) + el;
-                  const bool take = vv[jj][eh][el] < bv[eh] && (uint32_t)(ub[eh] + usgn * idx) <= dspan;
-                  if (take) { bv[eh] = vv[jj][eh][el]; bi[eh] = idx; if (WS) bs[eh] = ss[jj][eh][el]; }
-                }
+                  for (int el = 0; el < 2; ++el) {
+                    const int idx = 8 * (kNG * jg + jj) + el;
+                    bool take = vv[jj][eh][el] < bv[eh];
+                    if (decltype(masked_t)::value) take = take && (uint32_t)(ub[eh] + usgn * idx) <= dspan;
+                    if (take) { bv[eh] = vv[jj][eh][el]; bi[eh] = idx; if (WS) bs[eh] = ss[jj][eh][el]; }
+                  }
+            };
+            if (full_g >> jg & 1) update(std::false_type{});
+            else update(std::true_type{});
           }
         // best over the quad (the four t-lanes hold the other columns of the same windows)
 #pragma unroll
@@ -349,11 +355,15 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
 
 size_t corr_mma_best_bytes_per_pair(const DevJob& J) { return (size_t)J.nyc * J.nxc * (2 * sizeof(double) + sizeof(int)) + 768; }
 
+bool corr_mma_supported(const DevJob& J, int op) {
+  if (op == kOpSad) return false;                          // |a - b| is not a product
+  if (J.tw < 1 || J.tw > 32) return false;                 // K of one product; narrower templates zero the unused bytes of A
+  if (J.channels != 1 && J.channels != 3) return false;
+  return 255ll * 255 * J.n_elems < (1ll << 31);            // Sab must fit the s32 accumulators
+}
+
 cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaStream_t st) {
-  if (op == kOpSad) return cudaErrorNotSupported;        // |a - b| is not a product
-  if (J.tw != 16 && J.tw != 32) return cudaErrorNotSupported;
-  if (J.channels != 1 && J.channels != 3) return cudaErrorNotSupported;
-  if (255ll * 255 * J.n_elems >= (1ll << 31)) return cudaErrorNotSupported;  // Sab must fit the s32 accumulators
+  if (!corr_mma_supported(J, op)) return cudaErrorNotSupported;
   cfg.n_xtiles = (J.nxc + kMWin - 1) / kMWin;
   // bands: a band pays th - 1 warm-up rows (products only, about a quarter of a full row), a grid pays its last,
   // partly filled wave of 2 CTAs on each of the 148 SMs: take the band count with the best product of the two
@@ -387,7 +397,7 @@ cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaSt
   if (op == kOpSsd) USV_MMA_LAUNCH(TWW, NPLL, kOpSsd, false)                                               \
   else if (ws) USV_MMA_LAUNCH(TWW, NPLL, kOpCorr, true)                                                    \
   else USV_MMA_LAUNCH(TWW, NPLL, kOpCorr, false)
-  if (J.tw == 32) { if (npl == 1) USV_MMA_BY_OP(32, 1) else USV_MMA_BY_OP(32, 3) }
+  if (J.tw > 16) { if (npl == 1) USV_MMA_BY_OP(32, 1) else USV_MMA_BY_OP(32, 3) }
   else { if (npl == 1) USV_MMA_BY_OP(16, 1) else USV_MMA_BY_OP(16, 3) }
 #undef USV_MMA_BY_OP
 #undef USV_MMA_LAUNCH
