@@ -38,6 +38,10 @@ for t in range(n_cases):
     exp = oracle.match_dense(left, right, p)
     ok = all(np.array_equal(got[k], exp[k]) for k in ("right_index", "raw_cost", "disparity_u16"))
     ok = ok and got["matches"].tobytes() == exp["matches"].tobytes() and got["score"].tobytes() == exp["score"].tobytes()
+    # the same job without the score output: the tensor-pipe kernel then tracks only v = 1 - score (another instantiation)
+    g2 = ctx.match_dense(left, right, p, mask=_abi.OUT_MATCHES | _abi.OUT_DISPARITY_U16 | _abi.OUT_DISTANCE)
+    ok = ok and g2["matches"].tobytes() == exp["matches"].tobytes() and np.array_equal(g2["disparity_u16"], exp["disparity_u16"])
+    ok = ok and g2["distance"].tobytes() == got["distance"].tobytes()
     if not ok:
         bad += 1
         nb = int((got["right_index"] != exp["right_index"]).sum())
