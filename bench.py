@@ -266,29 +266,43 @@ def main():
     n_slots = n // pps
 
     def measure_e2e(out_mask, check):
-        # two batches in flight: the ring has two halves of n_slots slots; step k is submitted into half k & 1 before
-        # step k - 1 is waited for, so the copies of one step overlap the kernels of its neighbours (every step's H2D
-        # and D2H still run inside the timed region, and the region ends when the last step's results are on the host)
+        # up to two batches in flight: the ring has two halves of n_slots slots; with depth 2, step k is submitted into
+        # half k & 1 before step k - 1 is waited for, so the copies of one step overlap the kernels of its neighbours
+        # (every step's H2D and D2H still run inside the timed region, which ends when the last results are on the host)
         st = ctx.stream(frame, params, pairs_per_slot=pps, n_slots=2 * n_slots, mask=out_mask)
         for s in range(2 * n_slots):  # the capture side writes frames straight into the pinned ring
             a = (s % n_slots) * pps
             st.slots[s]["left"][:] = left[a:a + pps]
             st.slots[s]["right"][:] = right[a:a + pps]
 
-        def run_steps(k_steps):
+        def run_steps(k_steps, depth):
             for k in range(k_steps):
                 for s in range(n_slots):
                     st.submit((k & 1) * n_slots + s)
-                if k > 0:
+                if depth == 1:
+                    for s in range(n_slots):
+                        st.wait((k & 1) * n_slots + s)
+                elif k > 0:
                     for s in range(n_slots):
                         st.wait(((k - 1) & 1) * n_slots + s)
-            for s in range(n_slots):
-                st.wait(((k_steps - 1) & 1) * n_slots + s)
+            if depth == 2:
+                for s in range(n_slots):
+                    st.wait(((k_steps - 1) & 1) * n_slots + s)
 
-        run_steps(max(2, args.warmup))
+        # warm-up doubles as calibration of the pipeline depth: one GPU alone gains from two steps in flight, several
+        # GPUs behind one host lose when copies in both directions overlap all the time (scripts/pcie_probe.py)
+        t_cal = {}
+        for depth in (1, 2):
+            run_steps(1, depth)
+            barrier()
+            t0 = time.perf_counter()
+            run_steps(max(2, args.warmup), depth)
+            torch.cuda.synchronize()
+            t_cal[depth] = max_over_ranks(time.perf_counter() - t0)
+        depth = 1 if t_cal[1] <= t_cal[2] else 2
         barrier()
         t0 = time.perf_counter()
-        run_steps(args.steps)
+        run_steps(args.steps, depth)
         torch.cuda.synchronize()
         t = max_over_ranks(time.perf_counter() - t0)
         barrier()
@@ -296,15 +310,15 @@ def main():
         if rank == 0 and check:
             got = st.slots[0]["out"]["raw_cost_u16"][0, 100 * nx:101 * nx]
             ok = bool(np.array_equal(got, o_cost[100 * nx:101 * nx].cpu().numpy().view(np.uint16)))
-        res = (world * n * args.steps / t, st.h2d_bytes_per_pair * n, st.d2h_bytes_per_pair * n, ok)
+        res = (world * n * args.steps / t, st.h2d_bytes_per_pair * n, st.d2h_bytes_per_pair * n, ok, depth)
         st.close()
         return res
 
-    e2e_value, h2d, d2h, e2e_ok = measure_e2e(mask, True)
+    e2e_value, h2d, d2h, e2e_ok, e2e_depth = measure_e2e(mask, True)
     t_clk1 = time.time()  # the clock samples cover both timed regions (device-resident and e2e)
     # the same step with the 4-byte result record (the distance is a function of the disparity: the host can look it
     # up in the W-entry table): what the copies back to the host cost. Reported beside e2e, not instead of it.
-    c_value, c_h2d, c_d2h, _ = measure_e2e(_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST_U16, False)
+    c_value, c_h2d, c_d2h, _, c_depth = measure_e2e(_abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST_U16, False)
 
     clocks = None
     if rank == 0:
@@ -327,7 +341,7 @@ def main():
             "cand_evals_per_s": evals_s, "kernel": kernel_name, "gpu_launches": int(launches), "parity_vs_oracle": parity,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "cand_evals_per_s": e2e_value * ev_pair, "api": "usv_stream_submit/usv_stream_wait, %d slots x %d pairs per step, two steps in flight" % (n_slots, pps),
+                    "cand_evals_per_s": e2e_value * ev_pair, "api": "usv_stream_submit/usv_stream_wait, %d slots x %d pairs per step, %d step(s) in flight (calibrated in the warm-up)" % (n_slots, pps, e2e_depth),
                     "matches_device_path": e2e_ok,
                     "compact_results": {"value": c_value, "unit": "pairs/s", "h2d_bytes_per_step": int(c_h2d), "d2h_bytes_per_step": int(c_d2h),
                                         "outputs": "disparity_u16 + raw_cost_u16 per window (4 B); distance left to a host table lookup"}},
