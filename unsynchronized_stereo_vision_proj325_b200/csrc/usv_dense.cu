@@ -53,6 +53,7 @@ struct DenseCfg {
   int xb;           // bits of the candidate code inside the key
   int ring_words;   // shared-memory words of the row ring
   int x_off;        // tile t starts at x = t * stride_px - x_off (multiple of 4)
+  int n_pairs;      // the grid is one-dimensional: tile-major, heaviest tiles first (see the kernel)
 };
 
 __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c) {
@@ -311,7 +312,13 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
 
   const int tid = threadIdx.x, lane = tid & 31, p = tid >> 5;   // p: byte phase of this warp
   const int ul = lane & 3, dl = lane >> 2;
-  const int tile = blockIdx.x, band = blockIdx.y, pair = blockIdx.z;
+  // Block order = longest first: a tile's work grows with the number of disparities its windows can reach (LeftCam:
+  // with x, up to 20 passes against 2 for the full-range config), so all CTAs of the heaviest tile are dispatched
+  // first and the lightest tile fills the tail of the grid.
+  const int per_tile = cfg.n_bands * cfg.n_pairs;
+  const int t_ord = blockIdx.x / per_tile, rem = blockIdx.x - t_ord * per_tile;
+  const int tile = DIR < 0 ? cfg.n_xtiles - 1 - t_ord : t_ord;
+  const int pair = rem / cfg.n_bands, band = rem - pair * cfg.n_bands;
   const int X0 = tile * cfg.stride_px - cfg.x_off;  // LeftCam: the partial tile sits at the low-x end (fewest disparities)
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
@@ -421,7 +428,9 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   cfg.bh = (J.nyc + n_bands - 1) / n_bands;
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = (size_t)cfg.ring_words * 4 + (size_t)cfg.bh * 512;
-  dim3 grid(cfg.n_xtiles, cfg.n_bands, n_pairs), block(kDenseThreads);
+  cfg.n_pairs = n_pairs;
+  if ((long long)cfg.n_xtiles * cfg.n_bands * n_pairs > 0x7fffffffll) return cudaErrorNotSupported;
+  dim3 grid(cfg.n_xtiles * cfg.n_bands * n_pairs), block(kDenseThreads);
 #define USV_DENSE_LAUNCH(D, NWW)                                                                          \
   {                                                                                                       \
     auto kfn = ring2 ? dense_sad_argmin_kernel<D, NWW, true> : dense_sad_argmin_kernel<D, NWW, false>;                                                         \
