@@ -77,7 +77,12 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
   const int q = w & 3, mi = w >> 2;  // quarter of the pass's columns, m16 tile
-  const int tile = blockIdx.x, band = blockIdx.y, pair = blockIdx.z;
+  // one-dimensional grid, longest CTAs first: an x-tile's work grows with the candidate columns its windows can reach
+  // (LeftCam: with x), so all CTAs of the heaviest tile are dispatched first and the lightest fill the grid's tail
+  const int per_tile = cfg.n_bands * cfg.n_launch_pairs;
+  const int t_ord = blockIdx.x / per_tile, t_rem = blockIdx.x - t_ord * per_tile;
+  const int tile = J.camera_side == USV_LEFT_CAM ? cfg.n_xtiles - 1 - t_ord : t_ord;
+  const int pair = t_rem / cfg.n_bands, band = t_rem - pair * cfg.n_bands;
   const int xm = kMWin * tile;
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
@@ -109,8 +114,8 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
   constexpr int kTasks = 2 * NPL * kChunks;
   static_assert(kTasks <= kMThreads - 96 && kPassCols == 3 * 96, "ring tasks on warps 0..4, statistics on warps 5..7");
   const bool t_on = tid < kTasks;
-  const int t_half = tid / (NPL * kChunks), t_rem = tid - t_half * (NPL * kChunks);
-  const int t_pl = t_rem / kChunks, t_c = t_rem - t_pl * kChunks;
+  const int t_half = tid / (NPL * kChunks), t_hrem = tid - t_half * (NPL * kChunks);
+  const int t_pl = t_hrem / kChunks, t_c = t_hrem - t_pl * kChunks;
   const bool t_left = t_c < kMLChunks;
   const int t_w0 = 4 * (t_left ? t_c : t_c - kMLChunks);
   const uint32_t* t_gp = reinterpret_cast<const uint32_t*>((t_left ? Lb : Rb) + (long long)t_pl * cfg.plane_stride);
@@ -385,7 +390,8 @@ cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaSt
   const bool ws = op == kOpCorr && J.out.score != nullptr;
   const size_t smem = (size_t)4 * npl * kMRowWords * 4 + (2 * kPassCols + 2 * kMWin) * sizeof(double2) +
                       2 * 4 * kMWin * (2 * sizeof(double) + sizeof(int));
-  const dim3 grid(cfg.n_xtiles, cfg.n_bands, np), block(kMThreads);
+  cfg.n_launch_pairs = np;
+  const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kMThreads);
 #define USV_MMA_LAUNCH(TWW, NPLL, OPP, WSS)                                                                \
   {                                                                                                        \
     auto kfn = dense_corr_mma_kernel<TWW, NPLL, OPP, WSS>;                                                 \
