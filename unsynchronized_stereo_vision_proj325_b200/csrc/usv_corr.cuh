@@ -9,6 +9,7 @@ constexpr int kNoX = 0x7fffffff;  // x' of "no candidate yet"
 // inner operation / scoring: correlation (NCC, ZNCC), SSD = Saa + Sbb - 2 Sab from the same products, or SAD with
 // VABSDIFF4 in place of IDP.4A (colour frames: the gray SAD sweep has its own integer-key kernel, usv_dense.cu)
 constexpr int kOpCorr = 0, kOpSsd = 1, kOpSad = 2;
+constexpr int kOpSsdInt = 3;  // tensor-pipe kernel only: SSD scored and compared as u32 (costs below 2^28), no f64 in the inner loop
 
 struct CorrCfg {
   const uint8_t* lp;   // planes of the left frames  [pair][plane][H][pitch]

@@ -65,6 +65,7 @@ __device__ __forceinline__ bool v_better(double v_o, int x_o, double v_m, int x_
 template <int TW, int NPL, int OP, bool WS>
 __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJob J, const CorrCfg cfg) {
   constexpr bool SSD = OP != kOpCorr;
+  constexpr bool ISSD = OP == kOpSsdInt;  // integer scoring: cost = Saa + Sbb - 2 Sab in u32
   constexpr int NB = TW == 32 ? kNTW + 2 : kNTW;  // B words a thread reads per plane row (k32: b1 of tile j = b0 of tile j + 2)
   constexpr int NA = TW == 32 ? 4 : 2;            // A words
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -294,6 +295,51 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
           bi[eh] = -1;
         }
         const double2* rs = s_rs + par * kPassCols + kWarpCols * q + 2 * t;
+        if (ISSD) {
+          // SSD as integers: the statistics hold (-Saa, 1) / (-Sbb, 1) (NaN outside the frame), so
+          // cost = Saa + Sbb - 2 Sab < 2^28 (checked on the host); a column outside the frame contributes 2^30 and
+          // its cost stays above 2^29, i.e. above every real one, and is discarded after the loop
+          uint32_t kw[2], bc[2] = {0xffffffffu, 0xffffffffu};
+#pragma unroll
+          for (int eh = 0; eh < 2; ++eh) kw[eh] = __double2uint_rn(-La[eh].x);
+#pragma unroll
+          for (int jg = 0; jg < kNTW / kNG; ++jg)
+            if (any_g >> jg & 1) {
+              uint32_t cc[kNG][2][2];
+#pragma unroll
+              for (int jj = 0; jj < kNG; ++jj) {
+                const int j = kNG * jg + jj;
+                const double r0 = rs[8 * j].x, r1 = rs[8 * j + 1].x;
+                const uint32_t sb0 = r0 != r0 ? (1u << 30) : __double2uint_rn(-r0), sb1 = r1 != r1 ? (1u << 30) : __double2uint_rn(-r1);
+#pragma unroll
+                for (int eh = 0; eh < 2; ++eh)
+#pragma unroll
+                  for (int el = 0; el < 2; ++el)
+                    cc[jj][eh][el] = kw[eh] + (el ? sb1 : sb0) - 2u * (uint32_t)acc[j][2 * eh + el];
+              }
+              auto update = [&](auto masked_t) {
+#pragma unroll
+                for (int jj = 0; jj < kNG; ++jj)
+#pragma unroll
+                  for (int eh = 0; eh < 2; ++eh)
+#pragma unroll
+                    for (int el = 0; el < 2; ++el) {  // ascending x': a later equal candidate never replaces
+                      const int idx = 8 * (kNG * jg + jj) + el;
+                      bool take = cc[jj][eh][el] < bc[eh];
+                      if (decltype(masked_t)::value) take = take && (uint32_t)(ub[eh] + usgn * idx) <= dspan;
+                      if (take) { bc[eh] = cc[jj][eh][el]; bi[eh] = idx; }
+                    }
+              };
+              if (full_g >> jg & 1) update(std::false_type{});
+              else update(std::true_type{});
+            }
+#pragma unroll
+          for (int eh = 0; eh < 2; ++eh) {
+            const bool none = bc[eh] >= (1u << 29);
+            bv[eh] = none ? inf : __dadd_rn(1.0, (double)bc[eh]);  // v = 1 + SSD, as the f64 path carries it
+            if (none) bi[eh] = -1;
+          }
+        } else {
 #pragma unroll
         for (int jg = 0; jg < kNTW / kNG; ++jg)
           if (any_g >> jg & 1) {
@@ -331,6 +377,7 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
             if (full_g >> jg & 1) update(std::false_type{});
             else update(std::true_type{});
           }
+        }
         // best over the quad (the four t-lanes hold the other columns of the same windows)
 #pragma unroll
         for (int eh = 0; eh < 2; ++eh) {
@@ -388,6 +435,7 @@ cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaSt
   }
   const int npl = J.channels;
   const bool ws = op == kOpCorr && J.out.score != nullptr;
+  const bool ssd_int = 65025ll * J.n_elems < (1ll << 28);  // u32 scoring of SSD (the sentinel of out-of-frame columns is 2^30)
   const size_t smem = (size_t)4 * npl * kMRowWords * 4 + (2 * kPassCols + 2 * kMWin) * sizeof(double2) +
                       2 * 4 * kMWin * (2 * sizeof(double) + sizeof(int));
   cfg.n_launch_pairs = np;
@@ -400,7 +448,8 @@ cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaSt
     kfn<<<grid, block, smem, st>>>(J, cfg);                                                                \
   }
 #define USV_MMA_BY_OP(TWW, NPLL)                                                                           \
-  if (op == kOpSsd) USV_MMA_LAUNCH(TWW, NPLL, kOpSsd, false)                                               \
+  if (op == kOpSsd && ssd_int) USV_MMA_LAUNCH(TWW, NPLL, kOpSsdInt, false)                                 \
+  else if (op == kOpSsd) USV_MMA_LAUNCH(TWW, NPLL, kOpSsd, false)                                          \
   else if (ws) USV_MMA_LAUNCH(TWW, NPLL, kOpCorr, true)                                                    \
   else USV_MMA_LAUNCH(TWW, NPLL, kOpCorr, false)
   if (J.tw > 16) { if (npl == 1) USV_MMA_BY_OP(32, 1) else USV_MMA_BY_OP(32, 3) }
