@@ -335,6 +335,71 @@ __global__ void corr_rowsum_kernel(const uint8_t* __restrict__ frames, long long
   }
 }
 
+// The same row sums by prefix sums, one block per frame row: the row is read once with coalesced word loads (each thread
+// keeps its kScanWords words in registers), (sum, sum of squares) are scanned over the block, the exclusive prefix at every
+// pixel boundary goes to shared memory, and rs[y][x] = prefix[x + tw] - prefix[x] is written coalesced. Exact integers
+// (u32: a row of 8 192 bytes sums to < 2^30). Used when the row fits kScanThreads * kScanWords words.
+constexpr int kScanThreads = 256, kScanWords = 8;
+__global__ void __launch_bounds__(kScanThreads) corr_rowsum_scan_kernel(const uint8_t* __restrict__ frames, long long frame_stride, int row_stride,
+                                                                        int channels, int tw, int nxc, int width, int height, uint2* __restrict__ rs) {
+  extern __shared__ uint2 s_ps[];  // [width + 1]
+  __shared__ uint2 s_warp[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int y = blockIdx.x, pair = blockIdx.y;
+  const int nb = width * channels, nwords = (nb + 3) >> 2;
+  const int K = (nwords + kScanThreads - 1) / kScanThreads;  // words per thread (<= kScanWords, checked on the host)
+  const uint32_t* row = reinterpret_cast<const uint32_t*>(frames + (long long)pair * frame_stride + (long long)y * row_stride);
+  const int w0 = tid * K;
+  uint32_t wv[kScanWords];
+  uint32_t s1 = 0, s2 = 0;
+#pragma unroll
+  for (int k = 0; k < kScanWords; ++k) {
+    uint32_t w = 0;
+    if (k < K && w0 + k < nwords) {
+      w = __ldg(row + w0 + k);
+      const int left = nb - 4 * (w0 + k);  // bytes of this word inside the row
+      if (left < 4) w &= (1u << (8 * left)) - 1u;
+    }
+    wv[k] = w;
+    s1 = dp4a_u8(w, 0x01010101u, s1);
+    s2 = dp4a_u8(w, w, s2);
+  }
+  // exclusive block scan of the per-thread totals
+  uint32_t i1 = s1, i2 = s2;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, i1, o), b = __shfl_up_sync(0xffffffffu, i2, o);
+    if (lane >= o) { i1 += a; i2 += b; }
+  }
+  if (lane == 31) s_warp[wid] = make_uint2(i1, i2);
+  __syncthreads();
+  uint32_t p1 = i1 - s1, p2 = i2 - s2;
+  for (int k = 0; k < wid; ++k) { p1 += s_warp[k].x; p2 += s_warp[k].y; }
+  // walk the thread's bytes: the running prefix at every pixel boundary (also the one that closes the chunk; the next
+  // thread writes the same value there)
+  int b = 4 * w0;
+  int ph = b % channels, px = b / channels;  // byte b = channel ph of pixel px
+#pragma unroll
+  for (int k = 0; k < kScanWords; ++k) {
+    if (k < K) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ph == 0 && px <= width) s_ps[px] = make_uint2(p1, p2);
+        const uint32_t v = (wv[k] >> (8 * i)) & 0xffu;
+        p1 += v; p2 += v * v;
+        if (++ph == channels) { ph = 0; ++px; }
+      }
+    }
+  }
+  if (ph == 0 && px <= width) s_ps[px] = make_uint2(p1, p2);
+  __syncthreads();
+  uint2* o = rs + ((long long)pair * height + y) * nxc;
+  for (int x = tid; x < nxc; x += kScanThreads) {
+    const uint2 hi = s_ps[x + tw], lo = s_ps[x];
+    o[x] = make_uint2(hi.x - lo.x, hi.y - lo.y);
+  }
+}
+
 __global__ void corr_stats_kernel(const uint2* __restrict__ rs, int height, int tw, int th, int channels, int nxc, int nyc, int kind,
                                   int is_left, int band_rows, double2* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -447,9 +512,15 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
       const int band_rows = 64;
       const dim3 g1(((J.nxc + 31) / 32 + 63) / 64, J.height, np);
       const dim3 g2((J.nxc + 127) / 128, (J.nyc + band_rows - 1) / band_rows, np);
-      corr_rowsum_kernel<<<g1, 64, 0, st>>>(fl, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.height, rsum);
+      // row sums: prefix-sum kernel when the row fits one block's registers, else the sliding one
+      const bool scan = (J.width * J.channels + 3) / 4 <= kScanThreads * kScanWords;
+      const dim3 gs(J.height, np);
+      const size_t smem_scan = (size_t)(J.width + 1) * sizeof(uint2);
+      if (scan) corr_rowsum_scan_kernel<<<gs, kScanThreads, smem_scan, st>>>(fl, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.width, J.height, rsum);
+      else corr_rowsum_kernel<<<g1, 64, 0, st>>>(fl, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.height, rsum);
       corr_stats_kernel<<<g2, 128, 0, st>>>(rsum, J.height, J.tw, J.th, J.channels, J.nxc, J.nyc, J.cost_kind, 1, band_rows, st_l);
-      corr_rowsum_kernel<<<g1, 64, 0, st>>>(fr, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.height, rsum);
+      if (scan) corr_rowsum_scan_kernel<<<gs, kScanThreads, smem_scan, st>>>(fr, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.width, J.height, rsum);
+      else corr_rowsum_kernel<<<g1, 64, 0, st>>>(fr, J.frame_stride, J.row_stride, J.channels, J.tw, J.nxc, J.height, rsum);
       corr_stats_kernel<<<g2, 128, 0, st>>>(rsum, J.height, J.tw, J.th, J.channels, J.nxc, J.nyc, J.cost_kind, 0, band_rows, st_r);
       *n_launches += 4;
     }
