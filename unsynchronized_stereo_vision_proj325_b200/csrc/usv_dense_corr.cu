@@ -409,7 +409,9 @@ __global__ void corr_stats_kernel(const uint2* __restrict__ rs, int height, int 
   const uint2* col = rs + (long long)pair * height * nxc + x;
   const long long n = (long long)tw * th * channels;
   long long sa = 0, saa = 0;
+#pragma unroll 8
   for (int v = 0; v < th - 1; ++v) { const uint2 q = __ldg(col + (long long)(y0 + v) * nxc); sa += q.x; saa += q.y; }
+#pragma unroll 4
   for (int y = y0; y < y1; ++y) {
     const uint2 qin = __ldg(col + (long long)(y + th - 1) * nxc);
     sa += qin.x; saa += qin.y;
@@ -509,7 +511,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     double2* st_r = st_l + (size_t)np * J.nyc * J.nxc;
     uint2* rsum = (uint2*)(st_r + (size_t)np * J.nyc * J.nxc);  // [np][H][nxc], reused for the right camera
     {
-      const int band_rows = 64;
+      const int band_rows = 32;  // short bands: the kernel is latency-bound (one dependent load chain per thread)
       const dim3 g1(((J.nxc + 31) / 32 + 63) / 64, J.height, np);
       const dim3 g2((J.nxc + 127) / 128, (J.nyc + band_rows - 1) / band_rows, np);
       // row sums: prefix-sum kernel when the row fits one block's registers, else the sliding one
