@@ -25,7 +25,8 @@ struct CorrCfg {
   double* best_v;   // v = 1 - score
   double* best_sc;  // the score itself (only when the caller asked for it)
   int* best_x;
-  int n_launch_pairs;  // pairs of this launch (the grid is one-dimensional, tile-major)
+  int n_launch_pairs;  // pairs of this launch (the grid is one-dimensional: chunks of pairs, tile-major inside a chunk)
+  int chunk_pairs;
 };
 
 // (score, x') order of the reference: smaller cost v = 1 - score first, then smaller x' (P/Main.cpp:451)

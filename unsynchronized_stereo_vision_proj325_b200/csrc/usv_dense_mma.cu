@@ -78,12 +78,15 @@ __global__ void __launch_bounds__(kMThreads, 2) dense_corr_mma_kernel(const DevJ
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
   const int q = w & 3, mi = w >> 2;  // quarter of the pass's columns, m16 tile
-  // one-dimensional grid, longest CTAs first: an x-tile's work grows with the candidate columns its windows can reach
-  // (LeftCam: with x), so all CTAs of the heaviest tile are dispatched first and the lightest fill the grid's tail
-  const int per_tile = cfg.n_bands * cfg.n_launch_pairs;
-  const int t_ord = blockIdx.x / per_tile, t_rem = blockIdx.x - t_ord * per_tile;
+  // one-dimensional grid, chunks of pairs, inside a chunk the longest CTAs first: an x-tile's work grows with the
+  // candidate columns its windows can reach (LeftCam: with x), so all CTAs of the heaviest tile are dispatched first and
+  // the lightest fill the tail; the chunk keeps the tiles that read the same frame rows close in time (L2)
+  const int per_chunk = cfg.n_xtiles * cfg.n_bands * cfg.chunk_pairs;
+  const int chunk = blockIdx.x / per_chunk, crem = blockIdx.x - chunk * per_chunk;
+  const int per_tile = cfg.n_bands * min(cfg.chunk_pairs, cfg.n_launch_pairs - chunk * cfg.chunk_pairs);
+  const int t_ord = crem / per_tile, t_rem = crem - t_ord * per_tile;
   const int tile = J.camera_side == USV_LEFT_CAM ? cfg.n_xtiles - 1 - t_ord : t_ord;
-  const int pair = t_rem / cfg.n_bands, band = t_rem - pair * cfg.n_bands;
+  const int pair = chunk * cfg.chunk_pairs + t_rem / cfg.n_bands, band = t_rem % cfg.n_bands;
   const int xm = kMWin * tile;
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
@@ -439,6 +442,9 @@ cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaSt
   const size_t smem = (size_t)4 * npl * kMRowWords * 4 + (2 * kPassCols + 2 * kMWin) * sizeof(double2) +
                       2 * 4 * kMWin * (2 * sizeof(double) + sizeof(int));
   cfg.n_launch_pairs = np;
+  // one chunk: with bounded ranges most tiles weigh the same and the few light ones are worth more as the tail of the
+  // whole grid than L2 locality is (measured on C3: 2.65k pairs/s against 2.53k with 8-pair chunks; DRAM traffic is small)
+  cfg.chunk_pairs = np;
   const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kMThreads);
 #define USV_MMA_LAUNCH(TWW, NPLL, OPP, WSS)                                                                \
   {                                                                                                        \
