@@ -381,3 +381,19 @@ def test_unsynchronised_extrapolation(ctx, oracle):
                                         cen(res["tracks"][1]), cen(res["tracks"][0]), np.repeat(np.arange(4)[:, None], 3, 1),
                                         ns(t_other[2]), ns(t_other[1]), ns(t_other[0]))
     assert np.allclose(res["distance"], exp, rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cost,n", [("sad", 100), ("zncc", 70)])
+def test_many_pairs_block_order(ctx, oracle, cost, n):
+    """The dense kernels run a one-dimensional grid: chunks of up to 64 pairs, inside a chunk tile-major with the heaviest
+    x-tile first. More pairs than one chunk, the last chunk partly filled, several x-tiles and bands: every pair, every
+    window against the oracle."""
+    w, h = 150, 36
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost=cost)
+    left, right = synth.make_pairs(n, w, h, 1, shift=9, noise_sigma=2.0, seed=77)
+    got = ctx.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_DISPARITY_U16)
+    exp = oracle.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_DISPARITY_U16)
+    assert ctx.last_kernel == ("dense_sad_argmin_kernel" if cost == "sad" else "dense_corr_mma_kernel")
+    for k in ("right_index", "disparity_u16"):
+        assert np.array_equal(got[k], exp[k]), k
