@@ -255,9 +255,11 @@ def main():
         hbm_src = "measured"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
-    traffic = None
+    traffic, warp_inst_pair = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dense_traffic.json")))["dram_bytes_per_pair"] * n
+        rec = json.load(open(os.path.join(ROOT, "profiles", "dense_traffic.json")))
+        traffic = rec["dram_bytes_per_pair"] * n
+        warp_inst_pair = rec.get("warp_instructions_per_pair")  # executed warp-instructions, ncu on the same launch
     except Exception:
         pass
 
@@ -348,7 +350,13 @@ def main():
             "roofline": {"bound": "alu", "achieved": achieved_lane / 1e12, "peak": peak_lane / 1e12, "unit": "Tlaneop/s",
                          "frac": achieved_lane / peak_lane, "traffic": traffic,
                          "alu_ops_per_eval": ALU_OPS_PER_EVAL, "peak_source": "VABSDIFF4.U8.ACC issue rate measured in this run (usv_probe_issue_rate)",
-                         "direct_form_byteops_per_s": evals_s / world * TW * TH},
+                         "direct_form_byteops_per_s": evals_s / world * TW * TH,
+                         # how busy the SM's four issue ports are: executed warp-instructions (ncu count of this launch
+                         # shape) per second against 4 per clock and SM at the sampled clock
+                         "issue_slots": None if not (warp_inst_pair and clocks) else {
+                             "achieved_gwarpinst_per_s": value / world * warp_inst_pair / 1e9,
+                             "peak_gwarpinst_per_s": torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6 / 1e9,
+                             "frac": value / world * warp_inst_pair / (torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6)}},
             "roofline_hbm": {"bound": "hbm", "achieved": value / world * algo_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": value / world * algo_bytes / 1e9 / hbm_peak, "peak_source": hbm_src,
                              "algorithmic_bytes_per_pair": algo_bytes},
