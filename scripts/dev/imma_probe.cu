@@ -1,6 +1,7 @@
 // imma_probe.cu — issue rate of the legacy integer tensor path on sm_100a:
 // mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 from registers, CH independent accumulator chains per warp.
 // Prints MAC/clk/SM and T MAC/s for several warps-per-SM settings. Measurement aid, not product code.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/dev/imma_probe scripts/dev/imma_probe.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
