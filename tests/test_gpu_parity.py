@@ -397,3 +397,21 @@ def test_many_pairs_block_order(ctx, oracle, cost, n):
     assert ctx.last_kernel == ("dense_sad_argmin_kernel" if cost == "sad" else "dense_corr_mma_kernel")
     for k in ("right_index", "disparity_u16"):
         assert np.array_equal(got[k], exp[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("side", [0, 1])
+@pytest.mark.parametrize("lo,n_disp", [(0, 32), (0, 64), (0, 128), (0, 256), (4, 128), (5, 128), (-8, 64), (0, 125), (0, 29), (0, 1), (3, 4)])
+def test_bounded_ranges_thin_last_pass(ctx, oracle, side, lo, n_disp):
+    """Ranges whose length is a multiple of 32 (or up to 3 short of one) end in the thin pass of the SAD kernel (one
+    disparity per thread for the last 1..3 disparities of three of the four byte phases); neighbours of those lengths
+    and offsets that are not multiples of 4 take the regular path. Both camera sides, frames wide enough for interior
+    tiles (all runs equal) and edge tiles (range clipped by the frame)."""
+    w, h = 420, 30
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad", search_min=lo, search_max=lo + n_disp - 1, camera_side=side)
+    left, right = synth.make_pairs(2, w, h, 1, shift=21 if side == 0 else -21, noise_sigma=2.0, seed=5 + n_disp)
+    got = ctx.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST)
+    exp = oracle.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST)
+    assert ctx.last_kernel == "dense_sad_argmin_kernel"
+    for k in ("right_index", "raw_cost"):
+        assert np.array_equal(got[k], exp[k]), k

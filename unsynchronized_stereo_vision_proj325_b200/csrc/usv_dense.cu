@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // i0-1, i0-1-NW, ... and i1+NW-1, i1+2NW-1, ... start at BIG = 2^(31-xb) instead of 0. Every invalid
 // window then contains exactly one BIG column and its key carries bit 31 (true keys stay below 2^31,
 // checked on the host), every valid window contains none. No per-element masks, no second code path.
-template <int DIR, int NW, bool FOLD, bool RING2>
+template <int DIR, int NW, bool FOLD, bool RING2, int NJ = 4>
 __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
                                            const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
                                            const int XR0, const int run, const int dbase, const int r_shift,
@@ -92,10 +92,13 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const uint32_t minus_scale = key_scale * minus_one;  // -(1 << xb), kept opaque so the multiply stays an IMAD
   const uint32_t big = 1u << (31 - cfg.xb);
 
-  uint32_t code[4];
-  uint32_t V[8][4];
+  // NJ = 4: the regular pass (4 disparities per thread, 32 per warp). NJ = 1: the thin pass that closes a bounded range
+  // (only j = 0 is computed; lanes jh = 0 carry the four disparities D0 + p - 3 .. D0 + p the regular passes of this
+  // warp have not reached, lanes jh = 1 lie beyond dmax and are planted BIG) at about a third of a regular pass
+  uint32_t code[NJ];
+  uint32_t V[8][NJ];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int d = dbase + 4 * j;
     // x' of this thread's column 0; outside [-28, nxc-1] none of its 8 windows has a valid candidate at this d:
     // the code is then parked at 0 so that it can neither wrap nor spill into the cost bits
@@ -201,7 +204,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
+        for (int j = 0; j < NJ; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
     }
     if (HAS_OLD) {
       const int slot = RING2 ? (row & (2 * kRB - 1)) : slot_old;
@@ -214,7 +217,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
           V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
         }
@@ -222,10 +225,10 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
     if (HAS_KEYS) {
       uint32_t best[8];
 #pragma unroll
-      for (int jp = 0; jp < 4; jp += 2) {
+      for (int jp = 0; jp < NJ; jp += 2) {
         uint32_t key[2][8];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
+        for (int jj = 0; jj < (NJ == 1 ? 1 : 2); ++jj) {
           const int j = jp + jj;
           // columns 8 .. 8+NW-2 come from the next u-lane (garbage for ul = 3: those positions are not emitted)
           uint32_t Vx[8 + NW - 1];
@@ -248,7 +251,8 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) best[i] = jp == 0 ? min(key[0][i], key[1][i]) : __vimin3_u32(best[i], key[0][i], key[1][i]);
+        for (int i = 0; i < 8; ++i)
+          best[i] = NJ == 1 ? key[0][i] : jp == 0 ? min(key[0][i], key[1][i]) : __vimin3_u32(best[i], key[0][i], key[1][i]);
       }
       // reduce-scatter min over the 8 d-lanes (lane bits 4, 3, 2): 4 + 2 + 1 shuffles, each lane ends
       // with the minimum of one window
@@ -346,21 +350,31 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   // Passes each 32-px x-run (x-lane) needs. LeftCam runs further right reach further (d <= x): the last passes
   // of a tile keep only runs {1,2,3}, {2,3}, {3} busy.
   int n_run[4];
+  // Thin last pass: a warp's regular passes reach d_lo + 32n - 4 .. d_lo + 32n - 1 depending on its phase, so a range
+  // whose length is a multiple of 32 (128, 256: the usual ones) or up to 3 short of one would need a whole extra pass
+  // for its last 1 .. 3 disparities in three of the four warps. When every run of the tile is in that situation the
+  // last pass is run with one disparity per thread instead of four (dense_pass<..., NJ = 1>).
+  bool thin = true;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int xl = max(X0 + 32 * r, 0), xh = min(min(X0 + 32 * r + 31, X0 + cfg.stride_px - 1), J.nxc - 1);
     int dh;
     if (DIR < 0) dh = min(J.dmax, xh); else dh = min(J.dmax, J.nxc - 1 - xl);
     n_run[r] = (xh >= xl && dh >= d_lo) ? (dh - d_lo + 3) / 32 + 1 : 0;
+    if (n_run[r] > 0 && dh - d_lo > 32 * (n_run[r] - 1)) thin = false;  // the thin pass would not reach dh in every warp
   }
   const int n_all = max(max(n_run[0], n_run[1]), max(n_run[2], n_run[3]));
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (n_run[r] > 0 && n_run[r] != n_all) thin = false;
+  if (n_all == 0) thin = false;
   // Fold (LeftCam): run 3 never uses its neighbour's columns (the tile's last 3 positions are not emitted), so
   // its lane-0 slot in a pass where run 0 is already done can host run 3 of one of the tile's last passes,
   // which then need not run at all.
   int n_fold = 0;
   if (DIR < 0 && n_run[0] <= n_run[1] && n_run[1] <= n_run[2] && n_run[2] <= n_run[3] && n_run[3] - n_run[0] <= 3)
     n_fold = min(n_run[1] - n_run[0], n_run[3] - n_run[2]);
-  const int n_pass = n_all - n_fold;
+  const int n_pass = n_all - n_fold - (thin ? 1 : 0);  // thin implies equal runs, i.e. no fold
 
   for (int pass = 0; pass < n_pass; ++pass) {
     const int D0 = d_lo + 32 * pass;
@@ -375,6 +389,12 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     const int r_shift = DIR < 0 ? -((D0_mine - D0) >> 2) : ((D0_mine - D0) >> 2);
     if (fold_pass) dense_pass<DIR, NW, true, RING2>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
     else dense_pass<DIR, NW, false, RING2>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+  }
+  if (thin) {
+    const int D0 = d_lo + 32 * n_pass;
+    const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
+    const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
+    dense_pass<DIR, NW, false, RING2, 1>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, ul, dbase, 0, rows_in, minus_one);
   }
   __syncthreads();
 
