@@ -1,8 +1,8 @@
 // tcgen05_i8_probe.cu — issue rate of the Blackwell-native integer tensor path on sm_100a:
 // tcgen05.mma.cta_group::1.kind::i8, M = 128, N = 256, K = 32, u8 x u8 -> s32 accumulators in TMEM, both operands from
-// shared memory (K-major, no swizzle), issued by one thread per CTA, one CTA per SM. Operands are all ones, so every
-// accumulator must read 32 * (number of MMAs) — that checks the instruction descriptor and the TMEM read-back, not the
-// shared-memory layout. Measurement aid for DESIGN.md 4.1c (what a tcgen05 version of the row products would get over
+// shared memory (K-major, no swizzle), issued by one thread per CTA, one CTA per SM. Rate runs use all-ones operands (every
+// accumulator must read 32 * number of MMAs); layout_check() runs one MMA on non-uniform operands and compares all
+// 128 x 256 accumulators with the host, which pins the shared-memory descriptor and core-matrix layout as well. Measurement aid for DESIGN.md 4.1c (what a tcgen05 version of the row products would get over
 // the mma.sync one: scripts/dev/imma_probe.cu), not product code.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/dev/tcgen05_i8_probe scripts/dev/tcgen05_i8_probe.cu
 #include <cstdio>
@@ -81,11 +81,90 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int iters, int* out, unsi
   (void)lane;
 }
 
+// Layout check: one MMA on non-uniform operands, every accumulator read back and compared on the host. A[m][k] and
+// B[n][k] are written in the layout make_desc() describes: core matrix (row group rg = row / 8, K chunk kc = k / 16) at
+// (rg * 2 + kc) * 128 bytes, row r = row % 8 at r * 16 inside it, byte k % 16.
+__host__ __device__ inline uint8_t a_val(int m, int k) { return (uint8_t)(m * 3 + k * 5 + 1); }
+__host__ __device__ inline uint8_t b_val(int n, int k) { return (uint8_t)(n * 7 + k * 11 + 2); }
+__global__ void __launch_bounds__(128, 1) layout_check_kernel(int* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < kM * kK; i += 128) {
+    const int m = i / kK, k = i % kK;
+    smem[((m / 8) * 2 + k / 16) * 128 + (m % 8) * 16 + k % 16] = a_val(m, k);
+  }
+  for (int i = tid; i < kN * kK; i += 128) {
+    const int n = i / kK, k = i % kK;
+    smem[kABytes + ((n / 8) * 2 + k / 16) * 128 + (n % 8) * 16 + k % 16] = b_val(n, k);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t taddr = tmem_base;
+  const uint32_t idesc = (2u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+  if (tid == 0) {
+    const uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem + kABytes));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(taddr), "l"(da), "l"(db), "r"(idesc), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+  }
+  uint32_t done = 0;
+  for (long long spin = 0; spin < (1ll << 24) && !done; ++spin)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int c = 0; c < kN; ++c) {  // thread = accumulator row (TMEM lane), one column at a time
+    uint32_t v = 0;
+    const uint32_t a = taddr + ((uint32_t)(32 * warp) << 16) + c;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(a) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    out[tid * kN + c] = done ? (int)v : -1;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+static int layout_check() {
+  int* d; cudaMalloc(&d, kM * kN * 4);
+  const size_t smem = kABytes + kBBytes;
+  cudaFuncSetAttribute(layout_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  layout_check_kernel<<<1, 128, smem>>>(d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("{\"layout_check\": \"error %s\"}\n", cudaGetErrorString(e)); return 1; }
+  static int h[kM * kN];
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  int bad = 0, first = -1;
+  for (int m = 0; m < kM; ++m)
+    for (int n = 0; n < kN; ++n) {
+      int ref = 0;
+      for (int k = 0; k < kK; ++k) ref += (int)a_val(m, k) * (int)b_val(n, k);
+      if (h[m * kN + n] != ref) { if (first < 0) first = m * kN + n; ++bad; }
+    }
+  printf("{\"layout_check\": \"D[m][n] = sum_k A[m][k] B[n][k], 128 x 256 x 32, K-major core matrices (8 rows x 16 B), LBO 128 B (K), SBO 256 B (rows)\", "
+         "\"mismatches\": %d, \"first_bad\": %d, \"got\": %d}\n", bad, first, first >= 0 ? h[first] : 0);
+  cudaFree(d);
+  return bad != 0;
+}
+
 int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
   const int sms = p.multiProcessorCount;
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", p.name, sms, khz);
+  layout_check();
   int* d_out; unsigned long long* d_cyc;
   cudaMalloc(&d_out, (size_t)sms * 128 * 4); cudaMalloc(&d_cyc, (size_t)sms * 8);
   const size_t smem = kABytes + kBBytes;
