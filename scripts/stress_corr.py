@@ -33,7 +33,7 @@ for t in range(n_cases):
     p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=str(rng.choice(["ncc", "zncc", "ssd"] if mma_only else ["ncc", "zncc", "ssd", "sad"])), search_min=lo, search_max=hi, camera_side=side,
                          accept_threshold=thr, distance_kind=int(rng.integers(0, 3)))
     got = ctx.match_dense(left, right, p)
-    dense += ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_corr_mma_kernel", "dense_sad_argmin_kernel")  # gray SAD has its own kernel
+    dense += ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_corr_mma_kernel", "dense_corr_umma_kernel", "dense_sad_argmin_kernel")  # gray SAD has its own kernel
     kernels[ctx.last_kernel] = kernels.get(ctx.last_kernel, 0) + 1
     exp = oracle.match_dense(left, right, p)
     ok = all(np.array_equal(got[k], exp[k]) for k in ("right_index", "raw_cost", "disparity_u16"))

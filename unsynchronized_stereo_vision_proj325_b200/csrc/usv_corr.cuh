@@ -39,5 +39,8 @@ __device__ __forceinline__ bool corr_better(double sc_o, int x_o, double sc_m, i
 cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaStream_t st);
 size_t corr_mma_best_bytes_per_pair(const DevJob& J);
 bool corr_mma_supported(const DevJob& J, int op);
+// usv_dense_umma.cu: the same sweep with the products on tcgen05 (opt-in)
+cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaStream_t st);
+bool corr_umma_supported(const DevJob& J, int op);
 
 }  // namespace usv

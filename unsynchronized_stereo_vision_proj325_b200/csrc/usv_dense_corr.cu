@@ -445,6 +445,8 @@ size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out) {
 
 // Measurement switch (USV_CORR_MMA=0 keeps every correlation sweep on the ALU kernel, for A/B timing); read once.
 static const bool g_corr_use_mma = [] { const char* e = getenv("USV_CORR_MMA"); return !(e && e[0] == '0'); }();
+// USV_CORR_UMMA=1: the tcgen05 version of the tensor-pipe sweep (usv_dense_umma.cu), opt-in
+static const bool g_corr_use_umma = [] { const char* e = getenv("USV_CORR_UMMA"); return e && e[0] == '1'; }();
 
 // Returns cudaErrorNotSupported when the job is outside the kernel's coverage (the caller then runs the direct form).
 cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
@@ -484,7 +486,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = ring_bytes + (size_t)cfg.bh * 128 * 12;
 
-  bool used_mma = false;
+  bool used_mma = false, used_umma = false;
   for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
     const int np = std::min(chunk, n_pairs - p0);
     uint8_t* base = (uint8_t*)d_scratch;
@@ -535,7 +537,12 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
       cfg.best_v = (double*)bb;
       cfg.best_sc = cfg.best_v + (size_t)np * J.nyc * J.nxc;
       cfg.best_x = (int*)(cfg.best_sc + (size_t)np * J.nyc * J.nxc);
-      cudaError_t e = mma_ok ? launch_corr_mma(J, cfg, op, np, st) : cudaErrorNotSupported;
+      cudaError_t e = cudaErrorNotSupported;
+      if (mma_ok && g_corr_use_umma && corr_umma_supported(J, op)) {
+        e = launch_corr_umma(J, cfg, op, np, st);
+        if (e == cudaSuccess) used_umma = true;
+      }
+      if (e == cudaErrorNotSupported) e = mma_ok ? launch_corr_mma(J, cfg, op, np, st) : cudaErrorNotSupported;
       if (e == cudaSuccess) {
         *n_launches += 1;
         used_mma = true;
@@ -570,7 +577,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  *kernel_name = used_mma ? "dense_corr_mma_kernel" : "dense_corr_argmin_kernel";
+  *kernel_name = used_umma ? "dense_corr_umma_kernel" : used_mma ? "dense_corr_mma_kernel" : "dense_corr_argmin_kernel";
   return cudaSuccess;
 }
 

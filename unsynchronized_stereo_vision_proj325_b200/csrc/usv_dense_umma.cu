@@ -1,0 +1,310 @@
+// usv_dense_umma.cu — the correlation sweep of usv_dense_mma.cu with the row products on tcgen05 (UMMA):
+// tcgen05.mma.cta_group::1.kind::i8, M = 128 windows, N = 192 candidate columns, K = 32 bytes of one plane row, u8 x u8 -> s32
+// accumulators in tensor memory. Measured rate of the instruction on B200: 8 192 MAC/clk/SM, 4.2x mma.sync
+// (scripts/dev/tcgen05_i8_probe.cu, which also pins the operand layout used here).
+//
+// Same mathematics as usv_dense_mma.cu: G_v[x, x'] = sum_c L[v][x + c] R[v][x' + c] per plane row, slid down the rows.
+// UMMA reads its operands from shared memory in the canonical K-major layout (core matrices of 8 rows x 16 bytes), so
+// the Toeplitz operands are materialised: row m of the A tile is the 32 bytes L[x_m .. x_m + 31] (bytes beyond the
+// template width zeroed), row n of the B tile the 32 bytes R[x'_n .. x'_n + 31]; a 16-byte chunk is five aligned global
+// words funnel-shifted by the byte phase. u8 x u8 products only add, so two accumulator sets live in TMEM: E = sum of G
+// over every row that has entered the band so far (columns 0..191), L = sum over the rows that have left (columns
+// 256..447); Sab = E - L in wrap-around u32 (the band height keeps both below 2^31). A thread of the scoring phase owns
+// ONE window (its TMEM lane) and 48 of the pass's 192 columns: tcgen05.ld brings 16 accumulators of each set at a time,
+// the f64 scoring is the one of usv_dense_mma.cu, there is no cross-lane reduction — four column quarters are merged
+// through shared memory, passes through the global running best.
+//
+// v0 structure: no warp specialisation, the phases of a row run one after the other for the whole CTA (build the tiles,
+// one thread issues the 3 + 3 MMAs and commits to an mbarrier, everybody waits, everybody scores). One CTA per SM (512
+// threads, all 512 TMEM columns). Opt-in with USV_CORR_UMMA=1 until it has earned the default.
+#include <algorithm>
+#include <cstdlib>
+
+#include "usv_corr.cuh"
+
+namespace usv {
+
+constexpr int kUThreads = 512;
+constexpr int kUWin = 128;                 // M: windows per CTA
+constexpr int kUCols = 192;                // N: candidate columns per pass
+constexpr int kUQCols = kUCols / 4;        // columns per scoring warp (four column quarters)
+constexpr int kUK = 32;                    // K: bytes of one plane row per product
+constexpr int kUATile = kUWin * kUK, kUBTile = kUCols * kUK, kUTile = kUATile + kUBTile;
+constexpr uint32_t kUTmemCols = 512, kUAccL = 256;
+
+__device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle; core matrix (row group rg, 16-byte K chunk kc) at (rg * 2 + kc) * 128 bytes
+__device__ __forceinline__ uint64_t u_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void u_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void u_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ bool u_better(double v_o, int x_o, double v_m, int x_m) { return v_o < v_m || (v_o == v_m && x_o < x_m); }
+
+template <int NPL, int OP, bool WS>
+__global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const DevJob J, const CorrCfg cfg) {
+  constexpr bool SSD = OP != kOpCorr;
+  extern __shared__ __align__(1024) uint8_t usmem[];
+  uint8_t* s_tiles = usmem;                                                        // [enter, leave][NPL][A 4 KB | B 6 KB]
+  double2* s_rs = reinterpret_cast<double2*>(usmem + 2 * NPL * kUTile);            // [192] (Sb, rb) of the output row
+  double* s_mv = reinterpret_cast<double*>(s_rs + kUCols);                         // [4 quarters][128 windows]
+  double* s_msc = s_mv + 4 * kUWin;
+  int* s_mx = reinterpret_cast<int*>(s_msc + 4 * kUWin);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mx + 4 * kUWin);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = warp & 3, cq = warp >> 2;
+  const int per_tile = cfg.n_bands * cfg.n_launch_pairs;
+  const int t_ord = blockIdx.x / per_tile, t_rem = blockIdx.x - t_ord * per_tile;
+  const bool leftcam = J.camera_side == USV_LEFT_CAM;
+  const int tile = leftcam ? cfg.n_xtiles - 1 - t_ord : t_ord;  // heaviest tiles first
+  const int pair = t_rem / cfg.n_bands, band = t_rem - pair * cfg.n_bands;
+  const int xm = kUWin * tile;
+  const int y0 = band * cfg.bh;
+  const int bh = min(cfg.bh, J.nyc - y0);
+  const int th = J.th, tw = J.tw;
+  const int rows_in = bh + th - 1;
+  const int nxc = J.nxc;
+  const int row_words = cfg.pitch >> 2;
+  const uint8_t* Lb = cfg.lp + (long long)pair * cfg.pair_stride + (long long)y0 * cfg.pitch;
+  const uint8_t* Rb = cfg.rp + (long long)pair * cfg.pair_stride + (long long)y0 * cfg.pitch;
+  const double2* stl = cfg.stat_l + (long long)pair * J.nyc * nxc;
+  const double2* str = cfg.stat_r + (long long)pair * J.nyc * nxc;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  const uint32_t dspan = (uint32_t)(J.dmax - J.dmin);
+
+  const int x_last = min(xm + kUWin - 1, nxc - 1);
+  int c_lo, c_hi;
+  if (leftcam) { c_lo = max(0, xm - J.dmax); c_hi = min(nxc - 1, x_last - J.dmin); }
+  else { c_lo = max(0, xm + J.dmin); c_hi = min(nxc - 1, x_last + J.dmax); }
+  const int col_base = c_lo & ~3;
+  const int n_pass = c_hi >= c_lo ? (c_hi - col_base) / kUCols + 1 : 1;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(u_smem(s_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(u_smem(s_tmem)), "n"(kUTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t taddr = *s_tmem;
+  // D = S32, A = B = unsigned 8 bit, both K-major, N = 192, M = 128
+  const uint32_t idesc = (2u << 4) | ((uint32_t)(kUCols >> 3) << 17) | ((uint32_t)(kUWin >> 4) << 24);
+  uint32_t bar_phase = 0;
+
+  // scoring role of this thread: window m of the CTA (TMEM lane), column quarter cq of the pass
+  const int m = 32 * lg + lane, x = xm + m;
+  const uint32_t t_lane = taddr + ((uint32_t)(32 * lg) << 16);
+  const double n_eff = cfg.n_eff, c0 = __dmul_rn(cfg.n_eff, -4503599627370496.0);
+  const int usgn = leftcam ? -1 : 1;
+
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int xcol0 = col_base + pass * kUCols;
+    const int qcol0 = xcol0 + kUQCols * cq;                       // x' of this thread's first column
+    const int ub = (leftcam ? x - qcol0 : qcol0 - x) - J.dmin;    // d - dmin there; column j moves it by -/+ j
+    bool first_e = true, first_l = true;                          // (thread 0) the first product of a set overwrites
+    for (int r = 0; r < rows_in; ++r) {
+      // ---- (a) operand tiles of the entering row r and of the leaving row r - th, statistics of the output row
+      constexpr int kRowChunks = 2 * (kUWin + kUCols);            // 16-byte chunks per (half, plane)
+      for (int k = tid; k < 2 * NPL * kRowChunks; k += kUThreads) {
+        const int half = k / (NPL * kRowChunks);
+        int rem = k - half * (NPL * kRowChunks);
+        const int pl = rem / kRowChunks;
+        rem -= pl * kRowChunks;
+        const int row_i = rem >> 1, kc = rem & 1;
+        const bool is_a = row_i < kUWin;
+        const int idx = is_a ? row_i : row_i - kUWin;
+        const int gr = r - (half ? th : 0);
+        if (gr < 0) continue;
+        const int src = (is_a ? xm + idx : xcol0 + idx) + 16 * kc;  // first byte of the chunk in the plane row (>= 0)
+        const uint32_t* gp = reinterpret_cast<const uint32_t*>((is_a ? Lb : Rb) + (long long)pl * cfg.plane_stride + (long long)gr * cfg.pitch);
+        const int w0 = src >> 2, sh = 8 * (src & 3);
+        uint32_t g[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) g[i] = __ldg(gp + min(w0 + i, row_words - 1));
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __funnelshift_r(g[i], g[i + 1], sh);
+        if (is_a) {  // bytes of A beyond the template width are zero: K = 32 serves every width up to 32
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int nb = tw - (16 * kc + 4 * i);
+            o[i] &= nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+          }
+        }
+        uint8_t* dst = s_tiles + (half * NPL + pl) * kUTile + (is_a ? 0 : kUATile) + ((idx >> 3) * 2 + kc) * 128 + (idx & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      if (r >= th - 1 && tid < kUCols) {
+        const int xk = xcol0 + tid;
+        s_rs[tid] = xk > nxc - 1 ? make_double2(nan, nan) : __ldg(str + (long long)(y0 + r - (th - 1)) * nxc + xk);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tiles are read through the async proxy
+      __syncthreads();
+      // ---- (b) one thread issues the products: E += G_r, L += G_{r - th}
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          const uint32_t ta = u_smem(s_tiles + pl * kUTile);
+          u_mma(taddr, u_desc(ta), u_desc(ta + kUATile), idesc, first_e ? 0u : 1u);
+          first_e = false;
+        }
+        if (r >= th) {
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl) {
+            const uint32_t ta = u_smem(s_tiles + (NPL + pl) * kUTile);
+            u_mma(taddr + kUAccL, u_desc(ta), u_desc(ta + kUATile), idesc, first_l ? 0u : 1u);
+            first_l = false;
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem(s_bar)) : "memory");
+      }
+      // ---- (c) everybody waits for the products (a descriptor mistake traps instead of hanging the GPU)
+      {
+        uint32_t done = 0;
+        const uint32_t parity = bar_phase & 1;
+        for (int spin = 0; !done; ++spin) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(u_smem(s_bar)), "r"(parity) : "memory");
+          if (spin > (1 << 24)) __trap();
+        }
+        ++bar_phase;
+      }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // ---- (d) scores of the output row: this thread's window against its 48 columns
+      if (r >= th - 1) {
+        const int yo = y0 + r - (th - 1);
+        const double2 La = __ldg(stl + (long long)yo * nxc + min(x, nxc - 1));
+        double bv = inf, bs = -inf;
+        int bi = -1;
+#pragma unroll 1
+        for (int ch = 0; ch < kUQCols / 16; ++ch) {
+          const int cc = kUQCols * cq + 16 * ch;  // column inside the pass
+          uint32_t e[16], l[16];
+          u_ld16(t_lane + cc, e);
+          if (r >= th) u_ld16(t_lane + kUAccL + cc, l);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {  // ascending x': a later equal candidate never replaces (P/Main.cpp:451)
+            const uint32_t sab = r >= th ? e[i] - l[i] : e[i];
+            const double2 Rr = s_rs[cc + i];
+            const double nsab = __fma_rn(n_eff, __hiloint2double(0x43300000, (int)sab), c0);  // n * Sab, exact
+            const double num = SSD ? __dadd_rn(__dadd_rn(La.x, Rr.x), nsab) : __fma_rn(La.x, Rr.x, nsab);
+            const double sc = SSD ? num : __dmul_rn(__dmul_rn(num, La.y), Rr.y);
+            const double v = __dsub_rn(1.0, sc);
+            const int j = 16 * ch + i;
+            if (v < bv && (uint32_t)(ub + usgn * j) <= dspan) { bv = v; bi = j; if (WS) bs = sc; }
+          }
+        }
+        s_mv[cq * kUWin + m] = bv;
+        s_mx[cq * kUWin + m] = bi < 0 ? kNoX : qcol0 + bi;
+        if (WS) s_msc[cq * kUWin + m] = bs;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // TMEM, tiles and statistics may be overwritten; the quarters' winners are complete
+      if (r >= th - 1 && tid < kUWin) {
+        const int xw = xm + tid, yo = y0 + r - (th - 1);
+        double v = s_mv[tid], sc = WS ? s_msc[tid] : 0.0;
+        int xr = s_mx[tid];
+#pragma unroll
+        for (int qq = 1; qq < 4; ++qq) {
+          const double vo = s_mv[qq * kUWin + tid];
+          const int xo = s_mx[qq * kUWin + tid];
+          if (u_better(vo, xo, v, xr)) { v = vo; xr = xo; if (WS) sc = s_msc[qq * kUWin + tid]; }
+        }
+        if (xw <= nxc - 1) {
+          const long long eidx = ((long long)pair * J.nyc + yo) * nxc + xw;
+          if (pass > 0) {
+            const double vo = cfg.best_v[eidx];
+            const int xo = cfg.best_x[eidx];
+            if (!u_better(v, xr, vo, xo)) { v = vo; xr = xo; if (WS) sc = cfg.best_sc[eidx]; }
+          }
+          if (pass < n_pass - 1) { cfg.best_v[eidx] = v; cfg.best_x[eidx] = xr; if (WS) cfg.best_sc[eidx] = sc; }
+          else {
+            const long long wi = (long long)yo * J.nx + xw;
+            const long long gi = (long long)(cfg.pair0 + pair) * J.n_templates + wi;
+            if (xr == kNoX) write_result(J, gi, (uint32_t)wi, xw, yo, -1, 0xffffffffu, 0.0, inf);
+            else if (SSD) {
+              const uint32_t raw = (uint32_t)__dsub_rn(v, 1.0);
+              write_result(J, gi, (uint32_t)wi, xw, yo, xr, raw, 0.0, normalised_cost(raw, USV_COST_SSD, J.n_elems));
+            } else write_result(J, gi, (uint32_t)wi, xw, yo, xr, 0xffffffffu, __dadd_rn(sc, 0.0), v);
+          }
+        }
+      }
+      // the merge above reads s_m*; the next row writes them only after two more barriers
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kUTmemCols) : "memory");
+}
+
+bool corr_umma_supported(const DevJob& J, int op) {
+  if (op == kOpSad) return false;
+  if (J.tw < 1 || J.tw > kUK) return false;
+  if (J.channels != 1 && J.channels != 3) return false;
+  return 255ll * 255 * J.n_elems < (1ll << 31);
+}
+
+cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaStream_t st) {
+  if (!corr_umma_supported(J, op)) return cudaErrorNotSupported;
+  cfg.n_xtiles = (J.nxc + kUWin - 1) / kUWin;
+  // E and L are running sums over the rows of a band: keep them below 2^31
+  const long long per_row = 65025ll * J.tw * J.channels;
+  const int bh_cap = (int)std::max<long long>(1, std::min<long long>(J.nyc, ((1ll << 31) - 1) / per_row - J.th));
+  {
+    const int slots = 148;
+    double best_eff = -1.0;
+    int best_nb = (J.nyc + bh_cap - 1) / bh_cap;
+    for (int nb = best_nb; nb <= std::max(best_nb, J.nyc / 8); ++nb) {
+      const int bh = (J.nyc + nb - 1) / nb, nbb = (J.nyc + bh - 1) / bh;
+      if (bh > bh_cap) continue;
+      const long long ctas = (long long)nbb * cfg.n_xtiles * np;
+      const long long waves = (ctas + slots - 1) / slots;
+      const double eff = (double)ctas / (double)(waves * slots) * bh / (bh + 0.2 * (J.th - 1));
+      if (eff > best_eff * 1.005) { best_eff = eff; best_nb = nbb; }
+    }
+    cfg.bh = (J.nyc + best_nb - 1) / best_nb;
+    cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
+  }
+  cfg.n_launch_pairs = np;
+  cfg.chunk_pairs = np;
+  const int npl = J.channels;
+  const bool ws = op == kOpCorr && J.out.score != nullptr;
+  const size_t smem = (size_t)2 * npl * kUTile + kUCols * sizeof(double2) + 4 * kUWin * (2 * sizeof(double) + sizeof(int)) + 32;
+  const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kUThreads);
+#define USV_UMMA_LAUNCH(NPLL, OPP, WSS)                                                                    \
+  {                                                                                                        \
+    auto kfn = dense_corr_umma_kernel<NPLL, OPP, WSS>;                                                     \
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    if (e != cudaSuccess) return e;                                                                        \
+    kfn<<<grid, block, smem, st>>>(J, cfg);                                                                \
+  }
+#define USV_UMMA_BY_OP(NPLL)                                                                               \
+  if (op == kOpSsd) USV_UMMA_LAUNCH(NPLL, kOpSsd, false)                                                   \
+  else if (ws) USV_UMMA_LAUNCH(NPLL, kOpCorr, true)                                                        \
+  else USV_UMMA_LAUNCH(NPLL, kOpCorr, false)
+  if (npl == 1) USV_UMMA_BY_OP(1) else USV_UMMA_BY_OP(3)
+#undef USV_UMMA_BY_OP
+#undef USV_UMMA_LAUNCH
+  return cudaGetLastError();
+}
+
+}  // namespace usv
