@@ -14,8 +14,10 @@
 // the f64 scoring is the one of usv_dense_mma.cu, there is no cross-lane reduction — four column quarters are merged
 // through shared memory, passes through the global running best.
 //
-// v0 structure: no warp specialisation, the phases of a row run one after the other for the whole CTA (build the tiles,
-// one thread issues the 3 + 3 MMAs and commits to an mbarrier, everybody waits, everybody scores). One CTA per SM (512
+// Structure: no warp specialisation; per row one thread issues the 3 + 3 MMAs of the row (tiles staged during the previous
+// row) and commits to an mbarrier, everybody builds the tiles of the next row in the other buffer while the tensor pipe
+// works, waits, and scores (chunks of 8 columns, the next chunk's tcgen05.ld in flight during the scoring of the
+// current one; chunks outside the warp's candidates are skipped); one __syncthreads per row. One CTA per SM (512
 // threads, all 512 TMEM columns). Opt-in with USV_CORR_UMMA=1 until it has earned the default.
 #include <algorithm>
 #include <cstdlib>
@@ -50,18 +52,23 @@ __device__ __forceinline__ void u_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void u_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ bool u_better(double v_o, int x_o, double v_m, int x_m) { return v_o < v_m || (v_o == v_m && x_o < x_m); }
 
 template <int NPL, int OP, bool WS>
 __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const DevJob J, const CorrCfg cfg) {
   constexpr bool SSD = OP != kOpCorr;
   extern __shared__ __align__(1024) uint8_t usmem[];
-  uint8_t* s_tiles = usmem;                                                        // [enter, leave][NPL][A 4 KB | B 6 KB]
-  double2* s_rs = reinterpret_cast<double2*>(usmem + 2 * NPL * kUTile);            // [192] (Sb, rb) of the output row
-  double* s_mv = reinterpret_cast<double*>(s_rs + kUCols);                         // [4 quarters][128 windows]
-  double* s_msc = s_mv + 4 * kUWin;
-  int* s_mx = reinterpret_cast<int*>(s_msc + 4 * kUWin);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mx + 4 * kUWin);
+  uint8_t* s_tiles = usmem;                                                        // [2 buffers][enter, leave][NPL][A 4 KB | B 6 KB]
+  double2* s_rs = reinterpret_cast<double2*>(usmem + 4 * NPL * kUTile);            // [2][192] (Sb, rb) of the output row
+  double* s_mv = reinterpret_cast<double*>(s_rs + 2 * kUCols);                     // [2][4 quarters][128 windows]
+  double* s_msc = s_mv + 2 * 4 * kUWin;
+  int* s_mx = reinterpret_cast<int*>(s_msc + 2 * 4 * kUWin);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mx + 2 * 4 * kUWin);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = warp & 3, cq = warp >> 2;
@@ -119,64 +126,82 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
     const int qcol0 = xcol0 + kUQCols * cq;                       // x' of this thread's first column
     const int ub = (leftcam ? x - qcol0 : qcol0 - x) - J.dmin;    // d - dmin there; column j moves it by -/+ j
     bool first_e = true, first_l = true;                          // (thread 0) the first product of a set overwrites
-    for (int r = 0; r < rows_in; ++r) {
-      // ---- (a) operand tiles of the entering row r and of the leaving row r - th, statistics of the output row
-      constexpr int kRowChunks = 2 * (kUWin + kUCols);            // 16-byte chunks per (half, plane)
-      for (int k = tid; k < 2 * NPL * kRowChunks; k += kUThreads) {
-        const int half = k / (NPL * kRowChunks);
-        int rem = k - half * (NPL * kRowChunks);
-        const int pl = rem / kRowChunks;
-        rem -= pl * kRowChunks;
-        const int row_i = rem >> 1, kc = rem & 1;
+    // operand tiles of the entering row r and of the leaving row r - th (a task = the two 16-byte chunks of one tile row:
+    // nine aligned global words, funnel-shifted by the byte phase), statistics of the output row; buffer r & 1
+    auto stage = [&](int r) {
+      uint8_t* tiles = s_tiles + (r & 1) * 2 * NPL * kUTile;
+      constexpr int kRows = kUWin + kUCols;
+      for (int k = tid; k < 2 * NPL * kRows; k += kUThreads) {
+        const int half = k / (NPL * kRows);
+        int rem = k - half * (NPL * kRows);
+        const int pl = rem / kRows, row_i = rem - pl * kRows;
         const bool is_a = row_i < kUWin;
         const int idx = is_a ? row_i : row_i - kUWin;
         const int gr = r - (half ? th : 0);
         if (gr < 0) continue;
-        const int src = (is_a ? xm + idx : xcol0 + idx) + 16 * kc;  // first byte of the chunk in the plane row (>= 0)
+        const int src = is_a ? xm + idx : xcol0 + idx;  // first byte of the tile row in the plane row (>= 0)
         const uint32_t* gp = reinterpret_cast<const uint32_t*>((is_a ? Lb : Rb) + (long long)pl * cfg.plane_stride + (long long)gr * cfg.pitch);
         const int w0 = src >> 2, sh = 8 * (src & 3);
-        uint32_t g[5];
+        uint32_t g[9];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) g[i] = __ldg(gp + min(w0 + i, row_words - 1));
-        uint32_t o[4];
+        for (int i = 0; i < 9; ++i) g[i] = __ldg(gp + min(w0 + i, row_words - 1));
+        uint32_t o[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = __funnelshift_r(g[i], g[i + 1], sh);
+        for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(g[i], g[i + 1], sh);
         if (is_a) {  // bytes of A beyond the template width are zero: K = 32 serves every width up to 32
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int nb = tw - (16 * kc + 4 * i);
+          for (int i = 0; i < 8; ++i) {
+            const int nb = tw - 4 * i;
             o[i] &= nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
           }
         }
-        uint8_t* dst = s_tiles + (half * NPL + pl) * kUTile + (is_a ? 0 : kUATile) + ((idx >> 3) * 2 + kc) * 128 + (idx & 7) * 16;
+        uint8_t* dst = tiles + (half * NPL + pl) * kUTile + (is_a ? 0 : kUATile) + (idx >> 3) * 256 + (idx & 7) * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(o[4], o[5], o[6], o[7]);
       }
       if (r >= th - 1 && tid < kUCols) {
         const int xk = xcol0 + tid;
-        s_rs[tid] = xk > nxc - 1 ? make_double2(nan, nan) : __ldg(str + (long long)(y0 + r - (th - 1)) * nxc + xk);
+        s_rs[(r & 1) * kUCols + tid] = xk > nxc - 1 ? make_double2(nan, nan) : __ldg(str + (long long)(y0 + r - (th - 1)) * nxc + xk);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tiles are read through the async proxy
-      __syncthreads();
-      // ---- (b) one thread issues the products: E += G_r, L += G_{r - th}
+    };
+    // 8-column chunks of this warp's quarter that can hold a candidate of one of its 32 windows (warp-uniform)
+    uint32_t chunk_any = 0;
+    {
+      const int xw0 = xm + 32 * lg, xw1 = min(xw0 + 31, nxc - 1);
+      for (int ch = 0; ch < kUQCols / 8; ++ch) {
+        const int ca = qcol0 + 8 * ch, cb = ca + 7;
+        const int d_lo = leftcam ? xw0 - cb : ca - xw1, d_hi = leftcam ? xw1 - ca : cb - xw0;
+        if (xw0 <= nxc - 1 && ca <= c_hi && cb >= c_lo && d_hi >= J.dmin && d_lo <= J.dmax) chunk_any |= 1u << ch;
+      }
+    }
+    __syncthreads();  // the previous pass is done with every buffer
+    stage(0);
+    __syncthreads();
+    for (int r = 0; r < rows_in; ++r) {
+      const uint8_t* tiles = s_tiles + (r & 1) * 2 * NPL * kUTile;
+      // ---- one thread issues the products of row r: E += G_r, L += G_{r - th}
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int pl = 0; pl < NPL; ++pl) {
-          const uint32_t ta = u_smem(s_tiles + pl * kUTile);
+          const uint32_t ta = u_smem(tiles + pl * kUTile);
           u_mma(taddr, u_desc(ta), u_desc(ta + kUATile), idesc, first_e ? 0u : 1u);
           first_e = false;
         }
         if (r >= th) {
 #pragma unroll
           for (int pl = 0; pl < NPL; ++pl) {
-            const uint32_t ta = u_smem(s_tiles + (NPL + pl) * kUTile);
+            const uint32_t ta = u_smem(tiles + (NPL + pl) * kUTile);
             u_mma(taddr + kUAccL, u_desc(ta), u_desc(ta + kUATile), idesc, first_l ? 0u : 1u);
             first_l = false;
           }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem(s_bar)) : "memory");
       }
-      // ---- (c) everybody waits for the products (a descriptor mistake traps instead of hanging the GPU)
+      // ---- while the tensor pipe works: the tiles and statistics of the next row into the other buffer
+      if (r + 1 < rows_in) stage(r + 1);
+      // ---- everybody waits for the products (a descriptor mistake traps instead of hanging the GPU)
       {
         uint32_t done = 0;
         const uint32_t parity = bar_phase & 1;
@@ -188,46 +213,63 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
         ++bar_phase;
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- (d) scores of the output row: this thread's window against its 48 columns
+      // ---- scores of the output row: this thread's window against its 48 columns, 8 at a time; the accumulators of
+      // the next chunk are on their way from TMEM while the current one is scored
       if (r >= th - 1) {
         const int yo = y0 + r - (th - 1);
         const double2 La = __ldg(stl + (long long)yo * nxc + min(x, nxc - 1));
+        const double2* rs = s_rs + (r & 1) * kUCols + kUQCols * cq;
+        const bool has_l = r >= th;
         double bv = inf, bs = -inf;
         int bi = -1;
-#pragma unroll 1
-        for (int ch = 0; ch < kUQCols / 16; ++ch) {
-          const int cc = kUQCols * cq + 16 * ch;  // column inside the pass
-          uint32_t e[16], l[16];
-          u_ld16(t_lane + cc, e);
-          if (r >= th) u_ld16(t_lane + kUAccL + cc, l);
+        uint32_t e[2][8], l[2][8];
+        const uint32_t t_col = t_lane + kUQCols * cq;
+        int ch = chunk_any ? __ffs(chunk_any) - 1 : kUQCols / 8;
+        if (ch < kUQCols / 8) {
+          u_ld8(t_col + 8 * ch, e[0]);
+          if (has_l) u_ld8(t_col + kUAccL + 8 * ch, l[0]);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        int cur = 0;
+        while (ch < kUQCols / 8) {
+          const uint32_t rest = chunk_any & ~((2u << ch) - 1u);
+          const int nxt = rest ? __ffs(rest) - 1 : kUQCols / 8;
+          if (nxt < kUQCols / 8) {
+            if (cur == 0) { u_ld8(t_col + 8 * nxt, e[1]); if (has_l) u_ld8(t_col + kUAccL + 8 * nxt, l[1]); }
+            else { u_ld8(t_col + 8 * nxt, e[0]); if (has_l) u_ld8(t_col + kUAccL + 8 * nxt, l[0]); }
+          }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {  // ascending x': a later equal candidate never replaces (P/Main.cpp:451)
-            const uint32_t sab = r >= th ? e[i] - l[i] : e[i];
-            const double2 Rr = s_rs[cc + i];
+          for (int i = 0; i < 8; ++i) {  // ascending x': a later equal candidate never replaces (P/Main.cpp:451)
+            const uint32_t ee = cur == 0 ? e[0][i] : e[1][i], ll = cur == 0 ? l[0][i] : l[1][i];
+            const uint32_t sab = has_l ? ee - ll : ee;
+            const double2 Rr = rs[8 * ch + i];
             const double nsab = __fma_rn(n_eff, __hiloint2double(0x43300000, (int)sab), c0);  // n * Sab, exact
             const double num = SSD ? __dadd_rn(__dadd_rn(La.x, Rr.x), nsab) : __fma_rn(La.x, Rr.x, nsab);
             const double sc = SSD ? num : __dmul_rn(__dmul_rn(num, La.y), Rr.y);
             const double v = __dsub_rn(1.0, sc);
-            const int j = 16 * ch + i;
+            const int j = 8 * ch + i;
             if (v < bv && (uint32_t)(ub + usgn * j) <= dspan) { bv = v; bi = j; if (WS) bs = sc; }
           }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          ch = nxt;
+          cur ^= 1;
         }
-        s_mv[cq * kUWin + m] = bv;
-        s_mx[cq * kUWin + m] = bi < 0 ? kNoX : qcol0 + bi;
-        if (WS) s_msc[cq * kUWin + m] = bs;
+        const int mo = ((r & 1) * 4 + cq) * kUWin + m;
+        s_mv[mo] = bv;
+        s_mx[mo] = bi < 0 ? kNoX : qcol0 + bi;
+        if (WS) s_msc[mo] = bs;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // TMEM, tiles and statistics may be overwritten; the quarters' winners are complete
+      __syncthreads();  // TMEM and this row's buffers may be overwritten; the quarters' winners are complete
       if (r >= th - 1 && tid < kUWin) {
-        const int xw = xm + tid, yo = y0 + r - (th - 1);
-        double v = s_mv[tid], sc = WS ? s_msc[tid] : 0.0;
-        int xr = s_mx[tid];
+        const int xw = xm + tid, yo = y0 + r - (th - 1), mb = (r & 1) * 4 * kUWin;
+        double v = s_mv[mb + tid], sc = WS ? s_msc[mb + tid] : 0.0;
+        int xr = s_mx[mb + tid];
 #pragma unroll
         for (int qq = 1; qq < 4; ++qq) {
-          const double vo = s_mv[qq * kUWin + tid];
-          const int xo = s_mx[qq * kUWin + tid];
-          if (u_better(vo, xo, v, xr)) { v = vo; xr = xo; if (WS) sc = s_msc[qq * kUWin + tid]; }
+          const double vo = s_mv[mb + qq * kUWin + tid];
+          const int xo = s_mx[mb + qq * kUWin + tid];
+          if (u_better(vo, xo, v, xr)) { v = vo; xr = xo; if (WS) sc = s_msc[mb + qq * kUWin + tid]; }
         }
         if (xw <= nxc - 1) {
           const long long eidx = ((long long)pair * J.nyc + yo) * nxc + xw;
@@ -248,7 +290,6 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
           }
         }
       }
-      // the merge above reads s_m*; the next row writes them only after two more barriers
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -288,7 +329,7 @@ cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaS
   cfg.chunk_pairs = np;
   const int npl = J.channels;
   const bool ws = op == kOpCorr && J.out.score != nullptr;
-  const size_t smem = (size_t)2 * npl * kUTile + kUCols * sizeof(double2) + 4 * kUWin * (2 * sizeof(double) + sizeof(int)) + 32;
+  const size_t smem = (size_t)4 * npl * kUTile + 2 * kUCols * sizeof(double2) + 2 * 4 * kUWin * (2 * sizeof(double) + sizeof(int)) + 32;
   const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kUThreads);
 #define USV_UMMA_LAUNCH(NPLL, OPP, WSS)                                                                    \
   {                                                                                                        \
