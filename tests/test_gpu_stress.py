@@ -45,3 +45,14 @@ def test_alu_correlation_kernel_still_matches():
                        timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mismatches 0" in r.stdout and "dense_corr_mma_kernel" not in r.stdout
+
+
+def test_tcgen05_correlation_kernel_random_configs():
+    """USV_CORR_UMMA=1 routes the correlation sweeps to the tcgen05 kernel (usv_dense_umma.cu: UMMA kind::i8 products,
+    accumulators in tensor memory, operand tiles in the canonical K-major layout). Opt-in this round (it is slower than the
+    mma.sync kernel so far) but held to the same bar: every case bit-exact, every case on that kernel."""
+    env = dict(os.environ, USV_CORR_UMMA="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "stress_corr.py"), "60", "33", "mma"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mismatches 0" in r.stdout and "'dense_corr_umma_kernel': 60" in r.stdout
