@@ -10,15 +10,15 @@
 // words funnel-shifted by the byte phase. u8 x u8 products only add, so two accumulator sets live in TMEM: E = sum of G
 // over every row that has entered the band so far (columns 0..191), L = sum over the rows that have left (columns
 // 256..447); Sab = E - L in wrap-around u32 (the band height keeps both below 2^31). A thread of the scoring phase owns
-// ONE window (its TMEM lane) and 48 of the pass's 192 columns: tcgen05.ld brings 16 accumulators of each set at a time,
+// ONE window (its TMEM lane) and 24 of the pass's 192 columns: tcgen05.ld brings 8 accumulators of each set at a time,
 // the f64 scoring is the one of usv_dense_mma.cu, there is no cross-lane reduction — four column quarters are merged
 // through shared memory, passes through the global running best.
 //
 // Structure: no warp specialisation; per row one thread issues the 3 + 3 MMAs of the row (tiles staged during the previous
 // row) and commits to an mbarrier, everybody builds the tiles of the next row in the other buffer while the tensor pipe
-// works, waits, and scores (chunks of 8 columns, the next chunk's tcgen05.ld in flight during the scoring of the
-// current one; chunks outside the warp's candidates are skipped); one __syncthreads per row. One CTA per SM (512
-// threads, all 512 TMEM columns). Opt-in with USV_CORR_UMMA=1 until it has earned the default.
+// works, waits (one lane per warp polls), and scores (chunks of 8 columns; chunks outside the warp's candidates are
+// skipped); one __syncthreads per row. One CTA per SM (1024 threads = 4 TMEM lane groups x 8 column parts, all 512 TMEM
+// columns). Opt-in with USV_CORR_UMMA=1 until it has earned the default.
 #include <algorithm>
 #include <cstdlib>
 
@@ -26,10 +26,11 @@
 
 namespace usv {
 
-constexpr int kUThreads = 512;
+constexpr int kUThreads = 1024;            // 32 warps: 4 TMEM lane groups x 8 column parts
 constexpr int kUWin = 128;                 // M: windows per CTA
 constexpr int kUCols = 192;                // N: candidate columns per pass
-constexpr int kUQCols = kUCols / 4;        // columns per scoring warp (four column quarters)
+constexpr int kUNQ = kUThreads / 128;      // column parts a pass is split into
+constexpr int kUQCols = kUCols / kUNQ;     // columns per scoring warp
 constexpr int kUK = 32;                    // K: bytes of one plane row per product
 constexpr int kUATile = kUWin * kUK, kUBTile = kUCols * kUK, kUTile = kUATile + kUBTile;
 constexpr uint32_t kUTmemCols = 512, kUAccL = 256;
@@ -65,10 +66,10 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
   extern __shared__ __align__(1024) uint8_t usmem[];
   uint8_t* s_tiles = usmem;                                                        // [2 buffers][enter, leave][NPL][A 4 KB | B 6 KB]
   double2* s_rs = reinterpret_cast<double2*>(usmem + 4 * NPL * kUTile);            // [2][192] (Sb, rb) of the output row
-  double* s_mv = reinterpret_cast<double*>(s_rs + 2 * kUCols);                     // [2][4 quarters][128 windows]
-  double* s_msc = s_mv + 2 * 4 * kUWin;
-  int* s_mx = reinterpret_cast<int*>(s_msc + 2 * 4 * kUWin);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mx + 2 * 4 * kUWin);
+  double* s_mv = reinterpret_cast<double*>(s_rs + 2 * kUCols);                     // [2][kUNQ column parts][128 windows]
+  double* s_msc = s_mv + 2 * kUNQ * kUWin;
+  int* s_mx = reinterpret_cast<int*>(s_msc + 2 * kUNQ * kUWin);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mx + 2 * kUNQ * kUWin);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = warp & 3, cq = warp >> 2;
@@ -128,6 +129,8 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
     bool first_e = true, first_l = true;                          // (thread 0) the first product of a set overwrites
     // operand tiles of the entering row r and of the leaving row r - th (a task = the two 16-byte chunks of one tile row:
     // nine aligned global words, funnel-shifted by the byte phase), statistics of the output row; buffer r & 1
+    // operand tiles of the entering row r and of the leaving row r - th (a task = one tile row = two 16-byte chunks:
+    // nine aligned global words, funnel-shifted by the byte phase), statistics of the output row; buffer r & 1
     auto stage = [&](int r) {
       uint8_t* tiles = s_tiles + (r & 1) * 2 * NPL * kUTile;
       constexpr int kRows = kUWin + kUCols;
@@ -143,12 +146,18 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
         const uint32_t* gp = reinterpret_cast<const uint32_t*>((is_a ? Lb : Rb) + (long long)pl * cfg.plane_stride + (long long)gr * cfg.pitch);
         const int w0 = src >> 2, sh = 8 * (src & 3);
         uint32_t g[9];
+        if (w0 + 8 <= row_words - 1) {
+          const uint32_t* gq = gp + w0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) g[i] = __ldg(gp + min(w0 + i, row_words - 1));
+          for (int i = 0; i < 9; ++i) g[i] = __ldg(gq + i);
+        } else {  // the tile row runs past the end of the plane row (columns beyond the frame): clamp
+#pragma unroll
+          for (int i = 0; i < 9; ++i) g[i] = __ldg(gp + min(w0 + i, row_words - 1));
+        }
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(g[i], g[i + 1], sh);
-        if (is_a) {  // bytes of A beyond the template width are zero: K = 32 serves every width up to 32
+        if (is_a && tw < kUK) {  // bytes of A beyond the template width are zero: K = 32 serves every width up to 32
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int nb = tw - 4 * i;
@@ -201,15 +210,18 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
       }
       // ---- while the tensor pipe works: the tiles and statistics of the next row into the other buffer
       if (r + 1 < rows_in) stage(r + 1);
-      // ---- everybody waits for the products (a descriptor mistake traps instead of hanging the GPU)
+      // ---- everybody waits for the products: lane 0 of every warp polls (a descriptor mistake traps instead of hanging)
       {
-        uint32_t done = 0;
-        const uint32_t parity = bar_phase & 1;
-        for (int spin = 0; !done; ++spin) {
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                       : "=r"(done) : "r"(u_smem(s_bar)), "r"(parity) : "memory");
-          if (spin > (1 << 24)) __trap();
+        if (lane == 0) {
+          uint32_t done = 0;
+          const uint32_t parity = bar_phase & 1;
+          for (int spin = 0; !done; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(u_smem(s_bar)), "r"(parity) : "memory");
+            if (spin > (1 << 24)) __trap();
+          }
         }
+        __syncwarp();
         ++bar_phase;
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -222,39 +234,31 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
         const bool has_l = r >= th;
         double bv = inf, bs = -inf;
         int bi = -1;
-        uint32_t e[2][8], l[2][8];
         const uint32_t t_col = t_lane + kUQCols * cq;
-        int ch = chunk_any ? __ffs(chunk_any) - 1 : kUQCols / 8;
-        if (ch < kUQCols / 8) {
-          u_ld8(t_col + 8 * ch, e[0]);
-          if (has_l) u_ld8(t_col + kUAccL + 8 * ch, l[0]);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
-        int cur = 0;
-        while (ch < kUQCols / 8) {
-          const uint32_t rest = chunk_any & ~((2u << ch) - 1u);
-          const int nxt = rest ? __ffs(rest) - 1 : kUQCols / 8;
-          if (nxt < kUQCols / 8) {
-            if (cur == 0) { u_ld8(t_col + 8 * nxt, e[1]); if (has_l) u_ld8(t_col + kUAccL + 8 * nxt, l[1]); }
-            else { u_ld8(t_col + 8 * nxt, e[0]); if (has_l) u_ld8(t_col + kUAccL + 8 * nxt, l[0]); }
-          }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {  // ascending x': a later equal candidate never replaces (P/Main.cpp:451)
-            const uint32_t ee = cur == 0 ? e[0][i] : e[1][i], ll = cur == 0 ? l[0][i] : l[1][i];
-            const uint32_t sab = has_l ? ee - ll : ee;
-            const double2 Rr = rs[8 * ch + i];
-            const double nsab = __fma_rn(n_eff, __hiloint2double(0x43300000, (int)sab), c0);  // n * Sab, exact
-            const double num = SSD ? __dadd_rn(__dadd_rn(La.x, Rr.x), nsab) : __fma_rn(La.x, Rr.x, nsab);
-            const double sc = SSD ? num : __dmul_rn(__dmul_rn(num, La.y), Rr.y);
-            const double v = __dsub_rn(1.0, sc);
-            const int j = 8 * ch + i;
-            if (v < bv && (uint32_t)(ub + usgn * j) <= dspan) { bv = v; bi = j; if (WS) bs = sc; }
+        for (int ch = 0; ch < kUQCols / 8; ++ch)
+          if (chunk_any >> ch & 1) {
+            uint32_t e[8], l[8];
+            u_ld8(t_col + 8 * ch, e);
+            if (has_l) u_ld8(t_col + kUAccL + 8 * ch, l);
+            else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) l[i] = 0u;  // nothing has left the windows yet (the first output row of the band)
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // ascending x': a later equal candidate never replaces (P/Main.cpp:451)
+              const uint32_t sab = e[i] - l[i];
+              const double2 Rr = rs[8 * ch + i];
+              const double nsab = __fma_rn(n_eff, __hiloint2double(0x43300000, (int)sab), c0);  // n * Sab, exact
+              const double num = SSD ? __dadd_rn(__dadd_rn(La.x, Rr.x), nsab) : __fma_rn(La.x, Rr.x, nsab);
+              const double sc = SSD ? num : __dmul_rn(__dmul_rn(num, La.y), Rr.y);
+              const double v = __dsub_rn(1.0, sc);
+              const int j = 8 * ch + i;
+              if (v < bv && (uint32_t)(ub + usgn * j) <= dspan) { bv = v; bi = j; if (WS) bs = sc; }
+            }
           }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          ch = nxt;
-          cur ^= 1;
-        }
-        const int mo = ((r & 1) * 4 + cq) * kUWin + m;
+        const int mo = ((r & 1) * kUNQ + cq) * kUWin + m;
         s_mv[mo] = bv;
         s_mx[mo] = bi < 0 ? kNoX : qcol0 + bi;
         if (WS) s_msc[mo] = bs;
@@ -262,11 +266,11 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // TMEM and this row's buffers may be overwritten; the quarters' winners are complete
       if (r >= th - 1 && tid < kUWin) {
-        const int xw = xm + tid, yo = y0 + r - (th - 1), mb = (r & 1) * 4 * kUWin;
+        const int xw = xm + tid, yo = y0 + r - (th - 1), mb = (r & 1) * kUNQ * kUWin;
         double v = s_mv[mb + tid], sc = WS ? s_msc[mb + tid] : 0.0;
         int xr = s_mx[mb + tid];
 #pragma unroll
-        for (int qq = 1; qq < 4; ++qq) {
+        for (int qq = 1; qq < kUNQ; ++qq) {
           const double vo = s_mv[mb + qq * kUWin + tid];
           const int xo = s_mx[mb + qq * kUWin + tid];
           if (u_better(vo, xo, v, xr)) { v = vo; xr = xo; if (WS) sc = s_msc[mb + qq * kUWin + tid]; }
@@ -329,7 +333,7 @@ cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaS
   cfg.chunk_pairs = np;
   const int npl = J.channels;
   const bool ws = op == kOpCorr && J.out.score != nullptr;
-  const size_t smem = (size_t)4 * npl * kUTile + 2 * kUCols * sizeof(double2) + 2 * 4 * kUWin * (2 * sizeof(double) + sizeof(int)) + 32;
+  const size_t smem = (size_t)4 * npl * kUTile + 2 * kUCols * sizeof(double2) + 2 * kUNQ * kUWin * (2 * sizeof(double) + sizeof(int)) + 32;
   const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kUThreads);
 #define USV_UMMA_LAUNCH(NPLL, OPP, WSS)                                                                    \
   {                                                                                                        \
