@@ -1,3 +1,4 @@
+# bench.py at N GPUs with the e2e pipeline depth pinned to 1, 2 and calibrated (usage: gpu_e2e_depth_ab.sh N)
 mkdir -p gpurun_out
 N=$1
 for d in 1 2 auto; do

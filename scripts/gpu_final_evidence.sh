@@ -1,3 +1,4 @@
+# The round-end evidence set on one B200: GPU suite, smoke, bench + reference arm, ncu launch list, tensor-pipe kernel capture, per-config table.
 mkdir -p gpurun_out
 nvidia-smi -L | head -1; nproc
 ( time timeout 1500 python -m pytest tests -q -m gpu -x ) > gpurun_out/pytest_gpu_r31.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_gpu_r31.log
