@@ -34,6 +34,7 @@ constexpr int kUQCols = kUCols / kUNQ;     // columns per scoring warp
 constexpr int kUK = 32;                    // K: bytes of one plane row per product
 constexpr int kUATile = kUWin * kUK, kUBTile = kUCols * kUK, kUTile = kUATile + kUBTile;
 constexpr uint32_t kUTmemCols = 512, kUAccL = 256;
+constexpr int kURawL = 176, kURawR = 256, kURaw = kURawL + kURawR;  // raw plane-row segments of one (half, plane)
 
 __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
   int* s_mx = reinterpret_cast<int*>(s_msc + 2 * kUNQ * kUWin);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_mx + 2 * kUNQ * kUWin);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  uint8_t* s_raw = reinterpret_cast<uint8_t*>(s_bar) + 32;      // [2 buffers][enter, leave][NPL][L 176 B | R 256 B], 16-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lg = warp & 3, cq = warp >> 2;
   const int per_tile = cfg.n_bands * cfg.n_launch_pairs;
@@ -84,7 +86,6 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
   const int th = J.th, tw = J.tw;
   const int rows_in = bh + th - 1;
   const int nxc = J.nxc;
-  const int row_words = cfg.pitch >> 2;
   const uint8_t* Lb = cfg.lp + (long long)pair * cfg.pair_stride + (long long)y0 * cfg.pitch;
   const uint8_t* Rb = cfg.rp + (long long)pair * cfg.pair_stride + (long long)y0 * cfg.pitch;
   const double2* stl = cfg.stat_l + (long long)pair * J.nyc * nxc;
@@ -129,48 +130,61 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
     bool first_e = true, first_l = true;                          // (thread 0) the first product of a set overwrites
     // operand tiles of the entering row r and of the leaving row r - th (a task = the two 16-byte chunks of one tile row:
     // nine aligned global words, funnel-shifted by the byte phase), statistics of the output row; buffer r & 1
-    // operand tiles of the entering row r and of the leaving row r - th (a task = one tile row = two 16-byte chunks:
-    // nine aligned global words, funnel-shifted by the byte phase), statistics of the output row; buffer r & 1
+    // Staging in two steps. (1) cp.async brings the raw plane-row segments a row needs (L: 160 bytes from xm, R: 224 bytes
+    // from xcol0, 16-byte granules; entering and leaving row, every plane) into shared memory two rows ahead — no
+    // registers, the global latency is off the critical path. (2) Thread t < 320 owns tile row t (A rows 0..127, B rows
+    // 0..191) of every (half, plane): nine words of the raw segment, eight funnel shifts by the byte phase, two 16-byte
+    // stores into the canonical layout. Threads 320..511 fetch the statistics of the output row.
+    const int xcol0a = xcol0 & ~15;
+    constexpr int kRawChunks = kURaw / 16;  // 27 per (half, plane)
+    auto fetch_raw = [&](int r) {
+      if (tid < 2 * NPL * kRawChunks) {
+        const int hp = tid / kRawChunks, c = tid - hp * kRawChunks;
+        const int half = hp / NPL, pl = hp - half * NPL;
+        const int gr = r - (half ? th : 0);
+        const bool is_l = c < kURawL / 16;
+        const int byte0 = is_l ? xm + 16 * c : xcol0a + 16 * (c - kURawL / 16);
+        if (gr >= 0 && byte0 < cfg.pitch)
+          cp_async16(s_raw + ((r & 1) * 2 * NPL + hp) * kURaw + 16 * c,
+                     (is_l ? Lb : Rb) + (long long)pl * cfg.plane_stride + (long long)gr * cfg.pitch + byte0);
+      }
+      cp_async_commit();
+    };
+    const bool st_on = tid < kUWin + kUCols, st_a = tid < kUWin;
+    const int st_idx = st_a ? tid : tid - kUWin;
+    const int st_off = st_a ? st_idx : kURawL + (xcol0 - xcol0a) + st_idx;  // first byte of the tile row in the raw segment
+    const int st_w0 = st_off >> 2, st_sh = 8 * (st_off & 3);
+    const int st_dst = (st_a ? 0 : kUATile) + (st_idx >> 3) * 256 + (st_idx & 7) * 16;
     auto stage = [&](int r) {
       uint8_t* tiles = s_tiles + (r & 1) * 2 * NPL * kUTile;
-      constexpr int kRows = kUWin + kUCols;
-      for (int k = tid; k < 2 * NPL * kRows; k += kUThreads) {
-        const int half = k / (NPL * kRows);
-        int rem = k - half * (NPL * kRows);
-        const int pl = rem / kRows, row_i = rem - pl * kRows;
-        const bool is_a = row_i < kUWin;
-        const int idx = is_a ? row_i : row_i - kUWin;
-        const int gr = r - (half ? th : 0);
-        if (gr < 0) continue;
-        const int src = is_a ? xm + idx : xcol0 + idx;  // first byte of the tile row in the plane row (>= 0)
-        const uint32_t* gp = reinterpret_cast<const uint32_t*>((is_a ? Lb : Rb) + (long long)pl * cfg.plane_stride + (long long)gr * cfg.pitch);
-        const int w0 = src >> 2, sh = 8 * (src & 3);
-        uint32_t g[9];
-        if (w0 + 8 <= row_words - 1) {
-          const uint32_t* gq = gp + w0;
+      if (st_on) {
 #pragma unroll
-          for (int i = 0; i < 9; ++i) g[i] = __ldg(gq + i);
-        } else {  // the tile row runs past the end of the plane row (columns beyond the frame): clamp
+        for (int half = 0; half < 2; ++half) {
+          if (r - (half ? th : 0) < 0) continue;
 #pragma unroll
-          for (int i = 0; i < 9; ++i) g[i] = __ldg(gp + min(w0 + i, row_words - 1));
-        }
-        uint32_t o[8];
+          for (int pl = 0; pl < NPL; ++pl) {
+            const uint32_t* raw = reinterpret_cast<const uint32_t*>(s_raw + ((r & 1) * 2 * NPL + half * NPL + pl) * kURaw) + st_w0;
+            uint32_t g[9];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(g[i], g[i + 1], sh);
-        if (is_a && tw < kUK) {  // bytes of A beyond the template width are zero: K = 32 serves every width up to 32
+            for (int i = 0; i < 9; ++i) g[i] = raw[i];
+            uint32_t o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int nb = tw - 4 * i;
-            o[i] &= nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+            for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(g[i], g[i + 1], st_sh);
+            if (st_a && tw < kUK) {  // bytes of A beyond the template width are zero: K = 32 serves every width up to 32
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int nb = tw - 4 * i;
+                o[i] &= nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (1u << (8 * nb)) - 1u;
+              }
+            }
+            uint8_t* dst = tiles + (half * NPL + pl) * kUTile + st_dst;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dst + 128) = make_uint4(o[4], o[5], o[6], o[7]);
           }
         }
-        uint8_t* dst = tiles + (half * NPL + pl) * kUTile + (is_a ? 0 : kUATile) + (idx >> 3) * 256 + (idx & 7) * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-      if (r >= th - 1 && tid < kUCols) {
-        const int xk = xcol0 + tid;
-        s_rs[(r & 1) * kUCols + tid] = xk > nxc - 1 ? make_double2(nan, nan) : __ldg(str + (long long)(y0 + r - (th - 1)) * nxc + xk);
+      } else if (r >= th - 1 && tid < kUWin + 2 * kUCols) {
+        const int c = tid - (kUWin + kUCols), xk = xcol0 + c;
+        s_rs[(r & 1) * kUCols + c] = xk > nxc - 1 ? make_double2(nan, nan) : __ldg(str + (long long)(y0 + r - (th - 1)) * nxc + xk);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tiles are read through the async proxy
     };
@@ -185,10 +199,17 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
       }
     }
     __syncthreads();  // the previous pass is done with every buffer
+    fetch_raw(0);
+    if (rows_in > 1) fetch_raw(1);
+    cp_async_wait_all();
+    __syncthreads();
     stage(0);
     __syncthreads();
     for (int r = 0; r < rows_in; ++r) {
       const uint8_t* tiles = s_tiles + (r & 1) * 2 * NPL * kUTile;
+      // the raw segments of row r + 2 into the raw buffer of row r (its tiles were built a row ago); complete and visible
+      // after this row's closing barrier, i.e. before stage(r + 2)
+      if (r + 2 < rows_in) fetch_raw(r + 2);
       // ---- one thread issues the products of row r: E += G_r, L += G_{r - th}
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -208,7 +229,8 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(u_smem(s_bar)) : "memory");
       }
-      // ---- while the tensor pipe works: the tiles and statistics of the next row into the other buffer
+      // ---- while the tensor pipe works: the tiles and statistics of the next row into the other buffer (its raw
+      // segments landed during the previous row), then the raw segments of the row after it into the buffer just read
       if (r + 1 < rows_in) stage(r + 1);
       // ---- everybody waits for the products: lane 0 of every warp polls (a descriptor mistake traps instead of hanging)
       {
@@ -263,6 +285,7 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
         s_mx[mo] = bi < 0 ? kNoX : qcol0 + bi;
         if (WS) s_msc[mo] = bs;
       }
+      cp_async_wait_all();  // the raw segments of row r + 1 (issued a row ago) are in shared memory
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();  // TMEM and this row's buffers may be overwritten; the quarters' winners are complete
       if (r >= th - 1 && tid < kUWin) {
@@ -333,7 +356,8 @@ cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaS
   cfg.chunk_pairs = np;
   const int npl = J.channels;
   const bool ws = op == kOpCorr && J.out.score != nullptr;
-  const size_t smem = (size_t)4 * npl * kUTile + 2 * kUCols * sizeof(double2) + 2 * kUNQ * kUWin * (2 * sizeof(double) + sizeof(int)) + 32;
+  const size_t smem = (size_t)4 * npl * kUTile + 2 * kUCols * sizeof(double2) + 2 * kUNQ * kUWin * (2 * sizeof(double) + sizeof(int)) + 64 +
+                      (size_t)4 * npl * kURaw;
   const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kUThreads);
 #define USV_UMMA_LAUNCH(NPLL, OPP, WSS)                                                                    \
   {                                                                                                        \
