@@ -4,3 +4,8 @@ for sel in "colour 32x32 ZNCC" "zncc gray 16x16"; do USV_CORR_UMMA=1 timeout 200
 import sys,json
 for l in sys.stdin:
     d=json.loads(l); print(d['config'], round(d['pairs_per_s'],1), d['kernel'])"; done
+USV_CORR_UMMA=1 timeout 400 python scripts/stress_corr.py 200 401 mma | tail -1
+USV_CORR_UMMA=1 timeout 200 python scripts/run_configs.py --only "ncc gray" 2>&1 | tail -2 | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['config'], round(d['pairs_per_s'],1), d['kernel'])"

@@ -26,14 +26,17 @@
 
 namespace usv {
 
-constexpr int kUThreads = 1024;            // 32 warps: 4 TMEM lane groups x 8 column parts
+// Two shapes, chosen by the number of planes (measured): one plane — N = 128, E and L take 256 TMEM columns, two CTAs of
+// 512 threads per SM overlap each other's phases (7.8 k pairs/s on the 640x480 gray full-range config against 5.9 k for
+// the other shape and 6.9 k for the mma.sync kernel); three planes — N = 192 in one CTA of 1 024 threads per SM (the
+// tiles of three planes make the narrower pass re-stage too much: C3 2.07 k against 1.88 k).
 constexpr int kUWin = 128;                 // M: windows per CTA
-constexpr int kUCols = 192;                // N: candidate columns per pass
-constexpr int kUNQ = kUThreads / 128;      // column parts a pass is split into
-constexpr int kUQCols = kUCols / kUNQ;     // columns per scoring warp
 constexpr int kUK = 32;                    // K: bytes of one plane row per product
-constexpr int kUATile = kUWin * kUK, kUBTile = kUCols * kUK, kUTile = kUATile + kUBTile;
-constexpr uint32_t kUTmemCols = 512, kUAccL = 256;
+constexpr int kUATile = kUWin * kUK;
+constexpr int u_cols(int npl) { return npl == 1 ? 128 : 192; }        // N: candidate columns per pass
+constexpr int u_threads(int npl) { return npl == 1 ? 512 : 1024; }    // 4 TMEM lane groups x (threads / 128) column parts
+constexpr int u_ctas(int npl) { return npl == 1 ? 2 : 1; }            // CTAs per SM (TMEM: 2 x 256 or 1 x 512 columns)
+constexpr int u_tile(int npl) { return kUATile + u_cols(npl) * kUK; }
 constexpr int kURawL = 176, kURawR = 256, kURaw = kURawL + kURawR;  // raw plane-row segments of one (half, plane)
 
 __device__ __forceinline__ uint32_t u_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -62,8 +65,10 @@ __device__ __forceinline__ void u_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 __device__ __forceinline__ bool u_better(double v_o, int x_o, double v_m, int x_m) { return v_o < v_m || (v_o == v_m && x_o < x_m); }
 
 template <int NPL, int OP, bool WS>
-__global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const DevJob J, const CorrCfg cfg) {
+__global__ void __launch_bounds__(u_threads(NPL), u_ctas(NPL)) dense_corr_umma_kernel(const DevJob J, const CorrCfg cfg) {
   constexpr bool SSD = OP != kOpCorr;
+  constexpr int kUThreads = u_threads(NPL), kUCols = u_cols(NPL), kUNQ = kUThreads / 128, kUQCols = kUCols / kUNQ, kUTile = u_tile(NPL);
+  constexpr uint32_t kUTmemCols = u_ctas(NPL) == 2 ? 256 : 512, kUAccL = kUTmemCols / 2;
   extern __shared__ __align__(1024) uint8_t usmem[];
   uint8_t* s_tiles = usmem;                                                        // [2 buffers][enter, leave][NPL][A 4 KB | B 6 KB]
   double2* s_rs = reinterpret_cast<double2*>(usmem + 4 * NPL * kUTile);            // [2][192] (Sb, rb) of the output row
@@ -240,7 +245,8 @@ __global__ void __launch_bounds__(kUThreads, 1) dense_corr_umma_kernel(const Dev
           for (int spin = 0; !done; ++spin) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(u_smem(s_bar)), "r"(parity) : "memory");
-            if (spin > (1 << 24)) __trap();
+            if (!done) __nanosleep(64);  // the polling warps must not take the issue slots of the staging warps
+            if (spin > (1 << 22)) __trap();
           }
         }
         __syncwarp();
@@ -338,7 +344,7 @@ cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaS
   const long long per_row = 65025ll * J.tw * J.channels;
   const int bh_cap = (int)std::max<long long>(1, std::min<long long>(J.nyc, ((1ll << 31) - 1) / per_row - J.th));
   {
-    const int slots = 148;
+    const int slots = 148 * u_ctas(J.channels);
     double best_eff = -1.0;
     int best_nb = (J.nyc + bh_cap - 1) / bh_cap;
     for (int nb = best_nb; nb <= std::max(best_nb, J.nyc / 8); ++nb) {
@@ -356,9 +362,9 @@ cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaS
   cfg.chunk_pairs = np;
   const int npl = J.channels;
   const bool ws = op == kOpCorr && J.out.score != nullptr;
-  const size_t smem = (size_t)4 * npl * kUTile + 2 * kUCols * sizeof(double2) + 2 * kUNQ * kUWin * (2 * sizeof(double) + sizeof(int)) + 64 +
-                      (size_t)4 * npl * kURaw;
-  const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kUThreads);
+  const size_t smem = (size_t)4 * npl * u_tile(npl) + 2 * u_cols(npl) * sizeof(double2) +
+                      2 * (u_threads(npl) / 128) * kUWin * (2 * sizeof(double) + sizeof(int)) + 64 + (size_t)4 * npl * kURaw;
+  const dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(u_threads(npl));
 #define USV_UMMA_LAUNCH(NPLL, OPP, WSS)                                                                    \
   {                                                                                                        \
     auto kfn = dense_corr_umma_kernel<NPLL, OPP, WSS>;                                                     \
