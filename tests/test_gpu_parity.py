@@ -249,7 +249,7 @@ def test_stream_slots_do_not_share_scratch(ctx, oracle, cost, c):
             st.slots[s]["left"][:] = left[a:a + pps].reshape(pps, h, w * c)
             st.slots[s]["right"][:] = right[a:a + pps].reshape(pps, h, w * c)
             st.submit(s)
-        assert ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_corr_mma_kernel")
+        assert ctx.last_kernel in ("dense_corr_argmin_kernel", "dense_corr_mma_kernel", "dense_corr_umma_kernel")
         for s in range(n_slots):
             st.wait(s)
             a = (rnd * n_slots + s) * pps
@@ -394,7 +394,7 @@ def test_many_pairs_block_order(ctx, oracle, cost, n):
     left, right = synth.make_pairs(n, w, h, 1, shift=9, noise_sigma=2.0, seed=77)
     got = ctx.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_DISPARITY_U16)
     exp = oracle.match_dense(left, right, p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_DISPARITY_U16)
-    assert ctx.last_kernel == ("dense_sad_argmin_kernel" if cost == "sad" else "dense_corr_mma_kernel")
+    assert ctx.last_kernel in (("dense_sad_argmin_kernel",) if cost == "sad" else ("dense_corr_mma_kernel", "dense_corr_umma_kernel"))
     for k in ("right_index", "disparity_u16"):
         assert np.array_equal(got[k], exp[k]), k
 

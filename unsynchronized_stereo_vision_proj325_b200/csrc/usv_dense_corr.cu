@@ -445,8 +445,9 @@ size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out) {
 
 // Measurement switch (USV_CORR_MMA=0 keeps every correlation sweep on the ALU kernel, for A/B timing); read once.
 static const bool g_corr_use_mma = [] { const char* e = getenv("USV_CORR_MMA"); return !(e && e[0] == '0'); }();
-// USV_CORR_UMMA=1: the tcgen05 version of the tensor-pipe sweep (usv_dense_umma.cu), opt-in
-static const bool g_corr_use_umma = [] { const char* e = getenv("USV_CORR_UMMA"); return e && e[0] == '1'; }();
+// The tcgen05 version of the tensor-pipe sweep (usv_dense_umma.cu). Unset: used where it is measured faster (one-plane
+// NCC / ZNCC on frames at least one x-tile wide); USV_CORR_UMMA=1: wherever it applies; USV_CORR_UMMA=0: never.
+static const int g_corr_umma_mode = [] { const char* e = getenv("USV_CORR_UMMA"); return !e ? -1 : e[0] == '1' ? 1 : e[0] == '0' ? 0 : -1; }();
 
 // Returns cudaErrorNotSupported when the job is outside the kernel's coverage (the caller then runs the direct form).
 cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
@@ -538,7 +539,8 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
       cfg.best_sc = cfg.best_v + (size_t)np * J.nyc * J.nxc;
       cfg.best_x = (int*)(cfg.best_sc + (size_t)np * J.nyc * J.nxc);
       cudaError_t e = cudaErrorNotSupported;
-      if (mma_ok && g_corr_use_umma && corr_umma_supported(J, op)) {
+      const bool umma_auto = J.channels == 1 && op == kOpCorr && J.nxc >= 128;
+      if (mma_ok && (g_corr_umma_mode == 1 || (g_corr_umma_mode < 0 && umma_auto)) && corr_umma_supported(J, op)) {
         e = launch_corr_umma(J, cfg, op, np, st);
         if (e == cudaSuccess) used_umma = true;
       }
