@@ -234,7 +234,7 @@ def test_stream_matches_oracle(ctx, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cost,c", [("zncc", 3), ("ssd", 1)])
+@pytest.mark.parametrize("cost,c", [("zncc", 3), ("ssd", 1), ("zncc", 1)])  # the last one: concurrent tcgen05 kernels (TMEM allocation across streams)
 def test_stream_slots_do_not_share_scratch(ctx, oracle, cost, c):
     """The sliding correlation kernel keeps planes and window statistics in a scratch buffer; slots of a stream run
     concurrently on their own CUDA streams and must each own one (several batches in flight, then compare)."""
