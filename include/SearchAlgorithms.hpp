@@ -7,8 +7,10 @@
 // (template-major, candidate-minor, P/Main.cpp:408-410), the accept test (`< 0.75`, :417) and
 // the strict-'>' replacement rule (:451) are the reference's.
 //
-// Out of scope here (contour pre-processing): MorphilogicalFilter,
-// ABSDiffSearch, ColourSearch, CannySearch.
+// The contour pre-processing family (MorphilogicalFilter, ABSDiffSearch, ColourSearch, CannySearch) is DECLARED
+// at the end of this header exactly as P/SearchAlgorithms.hpp:35-43 declares it, so that a translation unit
+// of the reference that names these functions compiles against this header; their bodies are OpenCV contour
+// code outside the block-search path and stay with the reference's own Main.cpp.
 #ifndef SearchAlgorithms_HPP
 #define SearchAlgorithms_HPP
 
@@ -88,5 +90,17 @@ int RectifyLightingGray(const usv::ImageView& SrcBGR, const short* Map1, const u
 
 // Last error text of the calling thread's GPU context ("" when none).
 const char* BlockSearchLastError();
+
+// ---- P/SearchAlgorithms.hpp:35-43, declarations kept verbatim in signature (cv:: spelled out: this header does
+// not force `using namespace cv` on its includer unless DistanceCalculator.hpp's reference-compatible mode does).
+// Not defined by libusv_b200: the reference compiles its own definitions (P/Main.cpp:510-721 is the CannySearch it
+// actually builds). BlockSearch above is the replacement for the scoring half of CannySearch.
+void MorphilogicalFilter(cv::Mat ThesholdImage);
+void ABSDiffSearch(cv::Mat* Gray, cv::Mat& ThesholdImage, cv::Mat* ImportPrev, cv::Mat& ExportPrev);
+void ColourSearch(cv::Mat* HSVImage, cv::Mat& ThesholdImage, ColourSearchParameters* SliderValue);
+int CannySearch(bool CameraSide, cv::Mat* ImportGrayThisCamera, std::vector<std::vector<cv::Point> >* ImportCannyUsefulContoursOtherCamera,
+                std::vector<cv::Point2f>* ImportVectorCenter_pointOtherCamera,
+                std::vector<std::vector<cv::Point> >& ExportCannyUsefulContoursThisCamera,
+                std::vector<cv::Point2f>& ExportVectorCenter_pointThisCamera, cv::Mat& ExportContourOverlay, cv::Mat& ExportDebugCannyImg);
 
 #endif /* SearchAlgorithms_HPP */

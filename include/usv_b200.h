@@ -138,6 +138,22 @@ const char *usv_last_error(const usv_ctx *ctx);
 int64_t usv_launch_count(const usv_ctx *ctx);
 /* name of the kernel variant the last match call dispatched to */
 const char *usv_last_kernel(const usv_ctx *ctx);
+/* Per-context options. USV_OPT_CORR_KERNEL picks the sweep that serves the dense
+ * NCC / ZNCC / SSD costs wherever it covers the job (a test and measurement aid:
+ * the parity suite runs the same inputs through each kernel); AUTO = the
+ * dispatch the library ships with. There is no environment-variable switch. */
+#define USV_OPT_CORR_KERNEL 1
+#define USV_CORR_KERNEL_AUTO 0
+#define USV_CORR_KERNEL_ALU 1      /* IDP.4A sliding sums (usv_dense_corr.cu)    */
+#define USV_CORR_KERNEL_MMA_SYNC 2 /* mma.sync IMMA      (usv_dense_mma.cu)     */
+#define USV_CORR_KERNEL_TCGEN05 3  /* tcgen05 / TMEM     (usv_dense_umma.cu)    */
+int usv_set_option(usv_ctx *ctx, int32_t key, int64_t value);
+/* Status word the kernels of this context can raise instead of trapping (today: a
+ * tcgen05 completion wait that exceeded its 10 s wall-clock bound). Returns USV_OK
+ * or USV_ERR_CUDA (and clears the word). The *_host entry points and
+ * usv_stream_wait check it themselves; callers of the asynchronous *_device entry
+ * points check it after synchronising their stream. */
+int usv_device_status(usv_ctx *ctx);
 
 /* ---- geometry (pure host arithmetic, no device needed) ------------------ */
 /* nx, ny: window grid; cand_evals: candidate evaluations per frame pair.  */
@@ -158,7 +174,12 @@ int usv_match_dense_host(usv_ctx *ctx, const uint8_t *h_left,
 /* ---- sparse templates: explicit (x, y) list, shared by all pairs -------- */
 /* cost_rows (optional): [n_pairs][n_templates][row_cap] u32 costs of every
  * candidate in scan order (SAD/SSD); score_rows likewise f64 (NCC/ZNCC).
- * Entries past a template's candidate count are left untouched. */
+ * Entries past a template's candidate count are left untouched.
+ * A template must fit the frame: 0 <= x <= width - tmpl_w, 0 <= y <= height -
+ * tmpl_h. The *_host entry point rejects a list that violates this
+ * (USV_ERR_INVALID_ARG); the *_device entry point cannot read a list that lives
+ * in HBM, so its kernel writes the "no candidate" record for such a template
+ * (RightIndex USV_NO_MATCH, MatchValue +inf) and touches no frame memory. */
 int usv_match_templates_device(usv_ctx *ctx, const uint8_t *d_left,
                                const uint8_t *d_right,
                                const usv_frame_desc *frame, int32_t n_pairs,

@@ -13,6 +13,7 @@
 #define USV_HAVE_OPENCV 1
 #else
 namespace cv {
+class Mat;  // named by the contour-search declarations of SearchAlgorithms.hpp; never defined or used by this library
 template <typename T> struct Point_ {
   T x, y;
   Point_() : x(0), y(0) {}

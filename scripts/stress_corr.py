@@ -1,5 +1,5 @@
 """Randomised parity stress of the sliding-window correlation kernel (NCC / ZNCC / SSD, gray and colour; SAD on colour frames) against the CPU oracle:
-bit-exact indices, disparities, f64 scores and MatchValues.  python scripts/stress_corr.py [n_cases] [seed]"""
+bit-exact indices, disparities, f64 scores and MatchValues.  python scripts/stress_corr.py [n_cases] [seed] [mma|all] [auto|alu|mma|tcgen05]"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -10,6 +10,8 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 mma_only = len(sys.argv) > 3 and sys.argv[3] == "mma"  # only the tensor-pipe kernel's coverage: 16 / 32-px templates, no SAD, wider frames
 ctx = api.Context(0)
+forced = sys.argv[4] if len(sys.argv) > 4 else "auto"  # auto | alu | mma | tcgen05: Context.corr_kernel (usv_set_option)
+ctx.corr_kernel(forced)
 bad = dense = 0
 kernels = {}
 for t in range(n_cases):

@@ -53,6 +53,33 @@ int main() {
         assert out.returncode == 0, out.stderr
 
 
+def test_reference_search_family_is_declared():
+    """a translation unit that names the contour-search family of P/SearchAlgorithms.hpp:35-43 compiles
+    against include/SearchAlgorithms.hpp (declarations only; the bodies stay with the reference's Main.cpp)."""
+    src = r'''
+#include "SearchAlgorithms.hpp"
+using namespace cv;
+void (*f1)(Mat) = &MorphilogicalFilter;
+void (*f2)(Mat*, Mat&, Mat*, Mat&) = &ABSDiffSearch;
+void (*f3)(Mat*, Mat&, ColourSearchParameters*) = &ColourSearch;
+int (*f4)(bool, Mat*, std::vector<std::vector<Point>>*, std::vector<Point2f>*, std::vector<std::vector<Point>>&,
+          std::vector<Point2f>&, Mat&, Mat&) = &CannySearch;
+int caller(bool side, Mat* gray, std::vector<std::vector<Point>>* oc, std::vector<Point2f>* op, Mat& overlay, Mat& dbg) {
+  std::vector<std::vector<Point>> mine; std::vector<Point2f> centres;
+  ColourSearchParameters s = {0, 0, 0, 179, 255, 255, 0, 0};
+  (void)s;
+  return CannySearch(side, gray, oc, op, mine, centres, overlay, dbg);   // P/Main.cpp:1398
+}
+int main() { return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "t.cpp")
+        open(p, "w").write(src)
+        out = subprocess.run(["/usr/bin/g++", "-std=c++14", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), p],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+
+
 @pytest.mark.gpu
 def test_host_binary_against_oracle(oracle):
     assert os.path.exists(BIN), "run __graft_entry__.build()"

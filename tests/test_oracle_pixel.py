@@ -125,6 +125,25 @@ def test_cv2_cross_check(oracle):
                 assert np.abs(res - mine).max() <= 1e-4
 
 
+def test_sad_against_cv2_norm_l1(oracle):
+    """cv2.matchTemplate has no SAD mode, so the headline cost gets its own third-party check: every candidate's cost of
+    a set of templates (gray and colour, odd sizes, frame edges) against cv2.norm(a, b, NORM_L1) of the two patches — an
+    implementation that shares nothing with the oracle's loops — and the winner against the first minimum of that row."""
+    cv2 = pytest.importorskip("cv2")
+    every = dict(search_min=-(1 << 20), search_max=1 << 20)
+    for c, tw, th, w, h in ((1, 16, 16, 160, 48), (3, 32, 32, 150, 40), (1, 7, 5, 61, 19), (3, 9, 4, 40, 12)):
+        left, right = synth.make_pairs(1, w, h, c, shift=11, noise_sigma=3.0, seed=70 + tw)
+        L, R = np.ascontiguousarray(left[0]), np.ascontiguousarray(right[0])
+        nxc, nyc = w - tw + 1, h - th + 1
+        tx, ty = [0, nxc - 1, nxc // 2, 11, 12], [0, nyc - 1, nyc // 2, 1, nyc - 1]
+        out = oracle.match_templates(left, right, tx, ty, _abi.make_params(tmpl_w=tw, tmpl_h=th, cost="sad", accept_threshold=2.0, **every), rows=True)
+        for i, (x, y) in enumerate(zip(tx, ty)):
+            a = np.ascontiguousarray(L[y:y + th, x:x + tw])
+            ref = np.array([cv2.norm(a, np.ascontiguousarray(R[y:y + th, xr:xr + tw]), cv2.NORM_L1) for xr in range(nxc)])
+            assert np.array_equal(out["cost_rows"][0, i, :nxc].astype(np.float64), ref)
+            assert out["raw_cost"][0, i] == ref.min() and out["right_index"][0, i] == y * nxc + int(np.argmin(ref))
+
+
 def test_empty_candidate_range(oracle):
     left, right = synth.make_pairs(1, 40, 16, 1, shift=3, seed=2)
     p = _abi.make_params(tmpl_w=8, tmpl_h=8, cost="sad", search_min=10, search_max=12)

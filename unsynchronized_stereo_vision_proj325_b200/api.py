@@ -6,6 +6,7 @@ CUDA device is usable, the calls raise.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -17,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libusv_b200.so")
 
 # every symbol include/usv_b200.h declares
 EXPORTS = (
-    "usv_abi_version", "usv_create", "usv_destroy", "usv_last_error", "usv_launch_count", "usv_last_kernel",
+    "usv_abi_version", "usv_create", "usv_destroy", "usv_last_error", "usv_launch_count", "usv_last_kernel", "usv_device_status", "usv_set_option",
     "usv_grid_dims", "usv_match_dense_device", "usv_match_dense_host", "usv_match_templates_device",
     "usv_match_templates_host", "usv_disparity_to_distance", "usv_moving_object_distance",
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
@@ -111,9 +112,12 @@ class Context:
             raise UsvError("usv_create(device=%d) failed with %d (%s)" % (
                 device, rc, {-3: "no usable sm_100 CUDA device; there is no CPU fallback"}.get(rc, "see status codes")))
         self.device = device
+        self._streams = weakref.WeakSet()  # open Streams: closed before the context (they borrow it)
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
+            for st in list(getattr(self, "_streams", ())):
+                st.close()
             _lib.usv_destroy(self._h)
         self._h = None
 
@@ -132,6 +136,13 @@ class Context:
     def _check(self, rc, what):
         if rc:
             raise UsvError("%s failed (%d): %s" % (what, rc, lib().usv_last_error(self._h).decode()))
+
+    def set_option(self, key, value):
+        self._check(lib().usv_set_option(self._h, C.c_int32(int(key)), C.c_int64(int(value))), "usv_set_option")
+
+    def corr_kernel(self, which):
+        """Test / measurement aid: "auto" | "alu" | "mma" | "tcgen05" — the sweep that serves dense NCC / ZNCC / SSD."""
+        self.set_option(1, {"auto": 0, "alu": 1, "mma": 2, "tcgen05": 3}[which])
 
     @property
     def launch_count(self):
@@ -311,6 +322,7 @@ class Stream:
         rc = lib().usv_stream_create(ctx._h, C.byref(frame), C.byref(params), C.c_int32(pairs_per_slot), C.c_int32(n_slots),
                                      C.c_uint32(mask), C.byref(self._h))
         ctx._check(rc, "usv_stream_create")
+        ctx._streams.add(self)
         self.frame = FrameDesc()
         lib().usv_stream_frame_desc(self._h, C.byref(self.frame))
         self.nx, self.ny, self.cand_evals = grid_dims(frame, params)
@@ -369,6 +381,7 @@ class Stream:
         if getattr(self, "_h", None) and _lib is not None:
             self.slots = []
             _lib.usv_stream_destroy(self._h)
+            self.ctx._streams.discard(self)
         self._h = None
 
     def __del__(self):

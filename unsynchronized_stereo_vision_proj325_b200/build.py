@@ -7,6 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libusv_b200.so")
+OBJ = os.path.join(HERE, "_obj")
 MICROBENCH = os.path.join(HERE, "usv_microbench")
 HOST_TEST = os.path.join(HERE, "usv_host_test")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -44,8 +45,22 @@ def build(force=False, verbose=False, ptxas_info=False):
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES]
     hosts = [os.path.join(CSRC, s) for s in HOST_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     extra = ["-Xptxas", "-v"] if ptxas_info else []
-    if force or _newer(LIB, srcs + hosts + hdrs):
-        logs.append(_run([NVCC] + ARCH + COMMON + extra + ["-shared", "-I", inc, "-o", LIB] + srcs + hosts, verbose))
+    # one object per source (only the changed ones are recompiled, in parallel), then one link: no relocatable device
+    # code crosses a file boundary
+    os.makedirs(OBJ, exist_ok=True)
+    todo = []
+    objs = []
+    for src in srcs + hosts:
+        obj = os.path.join(OBJ, os.path.relpath(src, CSRC).replace(os.sep, "_") + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + hdrs):
+            todo.append((src, obj))
+    if todo:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            logs.extend(ex.map(lambda so: _run([NVCC] + ARCH + COMMON + extra + ["-c", "-I", inc, "-o", so[1], so[0]], verbose), todo))
+    if todo or force or _newer(LIB, objs):
+        logs.append(_run([NVCC] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs, verbose))
     mb = os.path.join(CSRC, "usv_microbench.cu")
     if os.path.exists(mb) and (force or _newer(MICROBENCH, [mb])):
         logs.append(_run([NVCC] + ARCH + COMMON + ["-o", MICROBENCH, mb], verbose))

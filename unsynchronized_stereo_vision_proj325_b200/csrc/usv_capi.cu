@@ -43,6 +43,8 @@ cudaError_t launch_moving_object_distance(int camera_side, long long t_this, con
 cudaError_t launch_coordinate_position(int camera_side, const double* dist, const float* xy, long long n, double* xyz, cudaStream_t st);
 }  // namespace usv
 
+namespace usv { int g_sm_count = 148; }
+
 using usv::DevJob;
 
 struct DevBuf {
@@ -56,9 +58,17 @@ struct usv_ctx {
   char err[512] = {0};
   std::atomic<long long> launches{0};
   const char* last_kernel = "none";
-  // distance LUT cache (by kind), [lut_n] doubles
+  // distance LUT cache (by kind), [lut_n] doubles. Grow-only: a LUT that is replaced by a longer one stays allocated
+  // until usv_destroy (kernels in flight on other streams of this context may still read it)
   double* lut[3] = {nullptr, nullptr, nullptr};
   int lut_n[3] = {0, 0, 0};
+  std::vector<void*> retired;
+  // status word the kernels can raise (mapped pinned host memory: readable by the host without a copy)
+  int* h_status = nullptr;
+  int* d_status = nullptr;
+  int sm_count = 148;
+  int corr_kernel = USV_CORR_KERNEL_AUTO;
+  std::atomic<int> open_streams{0};  // usv_destroy refuses while a usv_stream of this context is alive
   // grow-only scratch for the host paths
   DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws, pre_ws, corr_ws;
 };
@@ -138,9 +148,21 @@ static int check_cost_u16(usv_ctx* ctx, const usv_frame_desc* f, const usv_searc
   return USV_OK;
 }
 
-static void fill_job(DevJob& J, const uint8_t* l, const uint8_t* r, const usv_frame_desc* f, const usv_search_params* p,
+// a kernel gave up (today: a tcgen05 completion wait beyond its wall-clock bound): report it once, as an error
+static int check_dev_status(usv_ctx* ctx) {
+  if (ctx->h_status && *(volatile int*)ctx->h_status != 0) {
+    const int s = *(volatile int*)ctx->h_status;
+    *(volatile int*)ctx->h_status = 0;
+    return fail(ctx, USV_ERR_CUDA, "device status %d: a kernel abandoned a wait (results of the affected call are invalid)", s);
+  }
+  return USV_OK;
+}
+
+static void fill_job(usv_ctx* ctx, DevJob& J, const uint8_t* l, const uint8_t* r, const usv_frame_desc* f, const usv_search_params* p,
                      const usv_outputs* o) {
   memset(&J, 0, sizeof(J));
+  J.status = ctx->d_status;
+  J.corr_kernel = ctx->corr_kernel;
   J.left = l; J.right = r;
   J.frame_stride = f->frame_stride;
   J.width = f->width; J.height = f->height; J.channels = f->channels; J.row_stride = f->row_stride;
@@ -161,7 +183,7 @@ static int ensure_lut(usv_ctx* ctx, int kind, int width, cudaStream_t st, const 
   if (kind == USV_DIST_NONE) return USV_OK;
   if (ctx->lut_n[kind] < width) {
     // (re)build on the device with the same device function the kernels use
-    if (ctx->lut[kind]) { CU(cudaStreamSynchronize(st)); CU(cudaFree(ctx->lut[kind])); ctx->lut[kind] = nullptr; }
+    if (ctx->lut[kind]) { ctx->retired.push_back(ctx->lut[kind]); ctx->lut[kind] = nullptr; ctx->lut_n[kind] = 0; }
     int n = width < 4096 ? 4096 : width;
     CU(cudaMalloc((void**)&ctx->lut[kind], sizeof(double) * n));
     CU(usv::launch_build_distance_lut(ctx->lut[kind], n, kind, st));
@@ -188,17 +210,31 @@ extern "C" int usv_create(int device, usv_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return USV_ERR_CUDA;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return USV_ERR_CUDA;
-  if (prop.major < 10) return USV_ERR_NO_DEVICE;  // sm_100a cubins only
+  // the library holds sm_100a cubins only (arch-specific, not forward compatible): any other part would fail every
+  // launch with "no kernel image", so it is refused here
+  if (prop.major != 10 || prop.minor != 0) return USV_ERR_NO_DEVICE;
   usv_ctx* c = new (std::nothrow) usv_ctx();
   if (!c) return USV_ERR_NOMEM;
   c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  usv::g_sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return USV_ERR_CUDA; }
+  if (cudaHostAlloc((void**)&c->h_status, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&c->d_status, c->h_status, 0) != cudaSuccess) {
+    if (c->h_status) cudaFreeHost(c->h_status);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return USV_ERR_CUDA;
+  }
+  *c->h_status = 0;
   *out = c;
   return USV_OK;
 }
 
 extern "C" int usv_destroy(usv_ctx* ctx) {
   if (!ctx) return USV_ERR_INVALID_ARG;
+  if (ctx->open_streams.load() > 0)
+    return fail(ctx, USV_ERR_INVALID_ARG, "%d usv_stream(s) of this context are still open: destroy them first", ctx->open_streams.load());
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->in_l, &ctx->in_r, &ctx->tx, &ctx->ty, &ctx->rows_u32, &ctx->rows_f64};
@@ -209,6 +245,8 @@ extern "C" int usv_destroy(usv_ctx* ctx) {
   if (ctx->pre_ws.p) cudaFree(ctx->pre_ws.p);
   if (ctx->corr_ws.p) cudaFree(ctx->corr_ws.p);
   for (double* l : ctx->lut) if (l) cudaFree(l);
+  for (void* l : ctx->retired) cudaFree(l);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return USV_OK;
@@ -217,6 +255,16 @@ extern "C" int usv_destroy(usv_ctx* ctx) {
 extern "C" const char* usv_last_error(const usv_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" int64_t usv_launch_count(const usv_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : -1; }
 extern "C" const char* usv_last_kernel(const usv_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+extern "C" int usv_set_option(usv_ctx* ctx, int32_t key, int64_t value) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (key == USV_OPT_CORR_KERNEL) {
+    if (value < USV_CORR_KERNEL_AUTO || value > USV_CORR_KERNEL_TCGEN05) return fail(ctx, USV_ERR_INVALID_ARG, "USV_OPT_CORR_KERNEL: value %lld", (long long)value);
+    ctx->corr_kernel = (int)value;
+    return USV_OK;
+  }
+  return fail(ctx, USV_ERR_INVALID_ARG, "unknown option %d", key);
+}
+extern "C" int usv_device_status(usv_ctx* ctx) { return ctx ? check_dev_status(ctx) : USV_ERR_INVALID_ARG; }
 
 extern "C" int usv_grid_dims(const usv_frame_desc* f, const usv_search_params* p, int32_t* nx, int32_t* ny, int64_t* cand_evals) {
   if (!f || !p) return USV_ERR_INVALID_ARG;
@@ -248,7 +296,7 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
   if (n_pairs == 0) return USV_OK;
   CU(cudaSetDevice(ctx->device));
   DevJob J;
-  fill_job(J, d_left, d_right, f, p, d_out);
+  fill_job(ctx, J, d_left, d_right, f, p, d_out);
   const bool sparse = d_tx != nullptr;
   if (sparse) {
     if (!d_ty || n_templates < 0) return fail(ctx, USV_ERR_INVALID_ARG, "bad template list");
@@ -399,7 +447,7 @@ static int match_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_righ
   if (d_rows) CU(cudaMemcpyAsync(h_cost_rows, d_rows, sizeof(uint32_t) * n_res * row_cap, cudaMemcpyDeviceToHost, st));
   if (d_srows) CU(cudaMemcpyAsync(h_score_rows, d_srows, sizeof(double) * n_res * row_cap, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  return USV_OK;
+  return check_dev_status(ctx);
 }
 
 extern "C" int usv_match_dense_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_right, const usv_frame_desc* frame,
@@ -736,6 +784,7 @@ struct Slot {
 
 struct usv_stream {
   usv_ctx* ctx = nullptr;
+  int device = 0;
   usv_frame_desc hf, df;
   usv_search_params params;
   int32_t pairs_per_slot = 0, n_slots = 0;
@@ -746,7 +795,7 @@ struct usv_stream {
 
 extern "C" int usv_stream_destroy(usv_stream* s) {
   if (!s) return USV_ERR_INVALID_ARG;
-  cudaSetDevice(s->ctx->device);
+  cudaSetDevice(s->device);
   for (Slot& sl : s->slots) {
     if (sl.st) cudaStreamSynchronize(sl.st);
     if (sl.h_l) cudaFreeHost(sl.h_l);
@@ -761,6 +810,7 @@ extern "C" int usv_stream_destroy(usv_stream* s) {
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.st) cudaStreamDestroy(sl.st);
   }
+  if (s->ctx) s->ctx->open_streams--;
   delete s;
   return USV_OK;
 }
@@ -778,7 +828,7 @@ extern "C" int usv_stream_create(usv_ctx* ctx, const usv_frame_desc* frame, cons
   CU(cudaSetDevice(ctx->device));
   usv_stream* s = new (std::nothrow) usv_stream();
   if (!s) return fail(ctx, USV_ERR_NOMEM, "out of host memory");
-  s->ctx = ctx; s->params = *params; s->pairs_per_slot = pairs_per_slot; s->n_slots = n_slots; s->mask = output_mask;
+  s->ctx = ctx; s->device = ctx->device; ctx->open_streams++; s->params = *params; s->pairs_per_slot = pairs_per_slot; s->n_slots = n_slots; s->mask = output_mask;
   s->n_win = (int64_t)nx * ny;
   // pinned staging keeps the frames tightly packed at a 128-byte pitch, the same layout as in HBM,
   // so each slot needs exactly one cudaMemcpyAsync per camera
@@ -850,6 +900,8 @@ static int check_host_frame(usv_stream* s, const usv_frame_desc* hf) {
   if (hf->width != s->hf.width || hf->height != s->hf.height || hf->channels != s->hf.channels ||
       hf->row_stride < hf->width * hf->channels)
     return fail(s->ctx, USV_ERR_INVALID_ARG, "frame geometry differs from the stream's");
+  if (hf->frame_stride < (int64_t)hf->row_stride * hf->height)
+    return fail(s->ctx, USV_ERR_INVALID_ARG, "frame_stride %lld smaller than one frame", (long long)hf->frame_stride);
   return USV_OK;
 }
 
@@ -950,7 +1002,7 @@ extern "C" int usv_stream_wait(usv_stream* s, int32_t slot) {
   if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
   usv_ctx* ctx = s->ctx;
   CU(cudaEventSynchronize(s->slots[slot].done));
-  return USV_OK;
+  return check_dev_status(ctx);
 }
 
 extern "C" int usv_stream_bytes_per_pair(const usv_stream* s, int64_t* h2d, int64_t* d2h) {

@@ -7,6 +7,9 @@
 
 namespace usv {
 
+// SMs of the device the library runs on (set by usv_create from cudaDeviceProp; B200: 148): grid sizing only
+extern int g_sm_count;
+
 // Everything a matching kernel needs, passed by value (fits the 4 KB param space).
 struct DevJob {
   const uint8_t* left;
@@ -29,7 +32,18 @@ struct DevJob {
   double* score_rows;
   int row_cap;
   const double* dist_lut;  // [width] distance by disparity (dense kernels), may be null
+  int corr_kernel;         // USV_CORR_KERNEL_* (usv_set_option): which correlation sweep to run; 0 = automatic
+  int* status;             // device-visible status word of the context (mapped host memory): a kernel that gives up
+                           // (a tcgen05 wait that exceeds its wall-clock bound) sets it instead of trapping
 };
+
+constexpr int kDevStatusUmmaTimeout = 1;
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // candidate range (ascending x') of the window at x; mirrors include/usv_b200.h
 __host__ __device__ inline void cand_range(int x, int nxc, int camera_side, int dmin, int dmax, int* lo, int* hi) {

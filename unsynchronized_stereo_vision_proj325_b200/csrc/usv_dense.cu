@@ -450,7 +450,7 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   int bh_max = (smem_budget - cfg.ring_words * 4) / 512;
   if (bh_max < 8) return cudaErrorNotSupported;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
-  while ((long long)n_bands * cfg.n_xtiles * n_pairs < 148 * 3 && n_bands < (J.nyc + 15) / 16) ++n_bands;
+  while ((long long)n_bands * cfg.n_xtiles * n_pairs < g_sm_count * 3 && n_bands < (J.nyc + 15) / 16) ++n_bands;
   cfg.bh = (J.nyc + n_bands - 1) / n_bands;
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = (size_t)cfg.ring_words * 4 + (size_t)cfg.bh * 512;

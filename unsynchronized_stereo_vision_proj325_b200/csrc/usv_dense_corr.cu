@@ -27,7 +27,6 @@
 // statistics of the row (8 windows, 11 positions) sit in registers, and the running best per window is the pair
 // (score, x') in shared memory.
 #include <algorithm>
-#include <cstdlib>
 
 #include "usv_corr.cuh"
 
@@ -443,12 +442,6 @@ size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out) {
   return planes + 2ull * J.nyc * J.nxc * sizeof(double2) + (size_t)J.height * J.nxc * sizeof(uint2) + 512 + corr_mma_best_bytes_per_pair(J);
 }
 
-// Measurement switch (USV_CORR_MMA=0 keeps every correlation sweep on the ALU kernel, for A/B timing); read once.
-static const bool g_corr_use_mma = [] { const char* e = getenv("USV_CORR_MMA"); return !(e && e[0] == '0'); }();
-// The tcgen05 version of the tensor-pipe sweep (usv_dense_umma.cu). Unset: used where it is measured faster (one-plane
-// NCC / ZNCC on frames at least one x-tile wide); USV_CORR_UMMA=1: wherever it applies; USV_CORR_UMMA=0: never.
-static const int g_corr_umma_mode = [] { const char* e = getenv("USV_CORR_UMMA"); return !e ? -1 : e[0] == '1' ? 1 : e[0] == '0' ? 0 : -1; }();
-
 // Returns cudaErrorNotSupported when the job is outside the kernel's coverage (the caller then runs the direct form).
 cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
                               int* n_launches) {
@@ -464,7 +457,9 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   // (usv_dense_mma.cu; any width up to 32, any height, not SAD), which is preferred where both apply
   const bool alu_ok = J.tw % 4 == 0 && (nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) && J.th <= 64 &&
                       255ll * 255 * J.n_elems < (1ll << 32);  // Sab must fit the u32 accumulators
-  const bool mma_ok = g_corr_use_mma && corr_mma_supported(J, op);
+  // J.corr_kernel (usv_set_option USV_OPT_CORR_KERNEL, a test / measurement aid): 0 = the dispatch below, otherwise the
+  // named sweep wherever it covers the job
+  const bool mma_ok = J.corr_kernel != USV_CORR_KERNEL_ALU && corr_mma_supported(J, op);
   if (!alu_ok && !mma_ok) return cudaErrorNotSupported;
   int pitch;
   const size_t per_pair = corr_scratch_bytes_per_pair(J, &pitch);
@@ -482,7 +477,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
   int bh_max = (int)((smem_budget - ring_bytes) / (128 * 12));
   if (bh_max < 8) return cudaErrorNotSupported;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
-  while ((long long)n_bands * cfg.n_xtiles * n_pairs < 148 * 2 && n_bands < (J.nyc + 15) / 16) ++n_bands;
+  while ((long long)n_bands * cfg.n_xtiles * n_pairs < g_sm_count * 2 && n_bands < (J.nyc + 15) / 16) ++n_bands;
   cfg.bh = (J.nyc + n_bands - 1) / n_bands;
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = ring_bytes + (size_t)cfg.bh * 128 * 12;
@@ -540,7 +535,7 @@ cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, siz
       cfg.best_x = (int*)(cfg.best_sc + (size_t)np * J.nyc * J.nxc);
       cudaError_t e = cudaErrorNotSupported;
       const bool umma_auto = J.channels == 1 && op == kOpCorr && J.nxc >= 128;
-      if (mma_ok && (g_corr_umma_mode == 1 || (g_corr_umma_mode < 0 && umma_auto)) && corr_umma_supported(J, op)) {
+      if (mma_ok && (J.corr_kernel == USV_CORR_KERNEL_TCGEN05 || (J.corr_kernel == USV_CORR_KERNEL_AUTO && umma_auto)) && corr_umma_supported(J, op)) {
         e = launch_corr_umma(J, cfg, op, np, st);
         if (e == cudaSuccess) used_umma = true;
       }

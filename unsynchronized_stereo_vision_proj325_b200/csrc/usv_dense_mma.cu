@@ -423,7 +423,7 @@ cudaError_t launch_corr_mma(const DevJob& J, CorrCfg cfg, int op, int np, cudaSt
   // bands: a band pays th - 1 warm-up rows (products only, about a quarter of a full row), a grid pays its last,
   // partly filled wave of 2 CTAs on each of the 148 SMs: take the band count with the best product of the two
   {
-    const int slots = 148 * 2;
+    const int slots = g_sm_count * 2;
     double best_eff = -1.0;
     int best_nb = 1;
     for (int nb = 1; nb <= std::max(1, J.nyc / 8); ++nb) {

@@ -237,16 +237,26 @@ __global__ void __launch_bounds__(u_threads(NPL), u_ctas(NPL)) dense_corr_umma_k
       // ---- while the tensor pipe works: the tiles and statistics of the next row into the other buffer (its raw
       // segments landed during the previous row), then the raw segments of the row after it into the buffer just read
       if (r + 1 < rows_in) stage(r + 1);
-      // ---- everybody waits for the products: lane 0 of every warp polls (a descriptor mistake traps instead of hanging)
+      // ---- everybody waits for the products: lane 0 of every warp polls. The wait is bounded by wall clock (10 s on
+      // %globaltimer, far beyond any profiler or sanitizer slow-down of a microsecond-scale product); a wait that still
+      // expires raises the context's status word, which the host turns into USV_ERR_CUDA, and the CTA runs on (its
+      // results are then meaningless, but nothing traps and the context stays usable)
       {
         if (lane == 0) {
           uint32_t done = 0;
           const uint32_t parity = bar_phase & 1;
+          unsigned long long t_start = 0;
           for (int spin = 0; !done; ++spin) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(u_smem(s_bar)), "r"(parity) : "memory");
-            if (!done) __nanosleep(64);  // the polling warps must not take the issue slots of the staging warps
-            if (spin > (1 << 22)) __trap();
+            if (!done) {
+              __nanosleep(64);  // the polling warps must not take the issue slots of the staging warps
+              if ((spin & 1023) == 1023) {
+                const unsigned long long now = global_timer_ns();
+                if (t_start == 0) t_start = now;
+                else if (now - t_start > 10000000000ull) { if (J.status) { *(volatile int*)J.status = kDevStatusUmmaTimeout; __threadfence_system(); } break; }
+              }
+            }
           }
         }
         __syncwarp();
@@ -344,7 +354,7 @@ cudaError_t launch_corr_umma(const DevJob& J, CorrCfg cfg, int op, int np, cudaS
   const long long per_row = 65025ll * J.tw * J.channels;
   const int bh_cap = (int)std::max<long long>(1, std::min<long long>(J.nyc, ((1ll << 31) - 1) / per_row - J.th));
   {
-    const int slots = 148 * u_ctas(J.channels);
+    const int slots = g_sm_count * u_ctas(J.channels);
     double best_eff = -1.0;
     int best_nb = (J.nyc + bh_cap - 1) / bh_cap;
     for (int nb = best_nb; nb <= std::max(best_nb, J.nyc / 8); ++nb) {

@@ -65,6 +65,12 @@ block_cost_argmin_direct(const DevJob J, int tmpl_pitch_words, int strip_pitch_w
   if (J.tx) { x = J.tx[t_idx]; y = J.ty[t_idx]; }
   else { x = (t_idx % J.nx) * J.sx; y = (t_idx / J.nx) * J.sy; }
   const long long g = (long long)pair * J.n_templates + t_idx;
+  // the device-pointer API cannot validate a template list that lives in HBM: a template that does not fit the frame
+  // gets the "no candidate" record (USV_NO_MATCH, MatchValue +inf) instead of an out-of-bounds strip (block-uniform exit)
+  if (x < 0 || x >= J.nxc || y < 0 || y >= J.nyc) {
+    if (tid == 0) write_result(J, g, (uint32_t)t_idx, x, y, -1, 0xffffffffu, 0.0, __longlong_as_double(0x7ff0000000000000ll));
+    return;
+  }
   const uint8_t* L = J.left + (long long)pair * J.frame_stride;
   const uint8_t* R = J.right + (long long)pair * J.frame_stride;
 

@@ -294,7 +294,7 @@ cudaError_t launch_preprocess(int device, const uint8_t* d_src, uint8_t* d_dst, 
     J.src = d_src + (long long)f0 * src_frame_stride;
     J.dst = d_dst + (long long)f0 * dst_frame_stride;
     if (!lighting) {
-      rectify_gray_kernel<<<dim3(std::min(bx, 148 * 8), nf), kPreThreads, 0, st>>>(J);
+      rectify_gray_kernel<<<dim3(std::min(bx, g_sm_count * 8), nf), kPreThreads, 0, st>>>(J);
       *n_launches += 1;
       continue;
     }
@@ -303,10 +303,10 @@ cudaError_t launch_preprocess(int device, const uint8_t* d_src, uint8_t* d_dst, 
     J.hist = (uint32_t*)(base + (size_t)chunk * frame_words * 4);
     J.lut = (uint8_t*)(J.hist + (size_t)chunk * 256);
     if ((e = cudaMemsetAsync(J.hist, 0, (size_t)nf * 256 * 4, st)) != cudaSuccess) return e;
-    const int bx1 = std::max(1, std::min(bx, (148 * 8 + nf - 1) / nf));  // few, fat CTAs: fewer global histogram atomics
+    const int bx1 = std::max(1, std::min(bx, (g_sm_count * 8 + nf - 1) / nf));  // few, fat CTAs: fewer global histogram atomics
     rectify_hsv_hist_kernel<<<dim3(bx1, nf), kPreThreads, 0, st>>>(J);
     equalize_lut_kernel<<<nf, 256, 0, st>>>(J);
-    hsv_gray_kernel<<<dim3(std::max(1, std::min(bx, (148 * 16 + nf - 1) / nf)), nf), kPreThreads, 0, st>>>(J);
+    hsv_gray_kernel<<<dim3(std::max(1, std::min(bx, (g_sm_count * 16 + nf - 1) / nf)), nf), kPreThreads, 0, st>>>(J);
     *n_launches += 3;
   }
   return cudaGetLastError();

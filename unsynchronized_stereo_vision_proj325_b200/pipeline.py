@@ -54,50 +54,55 @@ def match_streams(frames_left, t_left, frames_right, t_right, params, max_dt=1.0
     pending = []  # (slot, count) in submission order
     pool = None
     registered = []
-    if gather and ctx is not None:
-        for store in (frames_left, frames_right):
-            if store.flags["C_CONTIGUOUS"] and store.nbytes:
-                try:
-                    ctx.host_register(store)
-                    registered.append(store)
-                except api.UsvError:
-                    pass  # already page-locked by the caller (or not lockable): the copies still work, synchronously
-    if copy_threads > 1 and not gather:  # the "capture" memcpy into the pinned ring is the host-side bound of the stream: spread it
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(copy_threads)
+    try:
+        if gather and ctx is not None:
+            for store in (frames_left, frames_right):
+                if store.flags["C_CONTIGUOUS"] and store.nbytes:
+                    try:
+                        ctx.host_register(store)
+                        registered.append(store)
+                    except api.UsvError:
+                        pass  # already page-locked by the caller (or not lockable): the copies still work, synchronously
+        if copy_threads > 1 and not gather:  # the "capture" memcpy into the pinned ring is the host-side bound of the stream: spread it
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(copy_threads)
 
-    def drain_one():
-        slot, cnt = pending.pop(0)
-        st.wait(slot)
-        for k in outs:
-            outs[k].append(st.slots[slot]["out"][k][:cnt].copy())
+        def drain_one():
+            slot, cnt = pending.pop(0)
+            st.wait(slot)
+            for k in outs:
+                outs[k].append(st.slots[slot]["out"][k][:cnt].copy())
 
-    for b0 in range(0, n, pairs_per_slot):
-        slot = (b0 // pairs_per_slot) % n_slots
-        if len(pending) == n_slots:
-            drain_one()  # the oldest in-flight batch owns this slot
-        cnt = min(pairs_per_slot, n - b0)
-        if gather:
-            st.submit_gather(slot, frames_left, li[b0:b0 + cnt], frames_right, ri[b0:b0 + cnt])
+        for b0 in range(0, n, pairs_per_slot):
+            slot = (b0 // pairs_per_slot) % n_slots
+            if len(pending) == n_slots:
+                drain_one()  # the oldest in-flight batch owns this slot
+            cnt = min(pairs_per_slot, n - b0)
+            if gather:
+                st.submit_gather(slot, frames_left, li[b0:b0 + cnt], frames_right, ri[b0:b0 + cnt])
+                pending.append((slot, cnt))
+                continue
+            # "capture": the paired frames land in the slot's pinned buffers
+            sl, sr = st.slots[slot]["left"], st.slots[slot]["right"]
+            if pool is None:
+                sl[:cnt] = frames_left[li[b0:b0 + cnt]].reshape(cnt, h, w * c)
+                sr[:cnt] = frames_right[ri[b0:b0 + cnt]].reshape(cnt, h, w * c)
+            else:
+                list(pool.map(lambda k: (np.copyto(sl[k], frames_left[li[b0 + k]].reshape(h, w * c)),
+                                         np.copyto(sr[k], frames_right[ri[b0 + k]].reshape(h, w * c))), range(cnt)))
+            st.submit(slot, cnt)
             pending.append((slot, cnt))
-            continue
-        # "capture": the paired frames land in the slot's pinned buffers
-        sl, sr = st.slots[slot]["left"], st.slots[slot]["right"]
-        if pool is None:
-            sl[:cnt] = frames_left[li[b0:b0 + cnt]].reshape(cnt, h, w * c)
-            sr[:cnt] = frames_right[ri[b0:b0 + cnt]].reshape(cnt, h, w * c)
-        else:
-            list(pool.map(lambda k: (np.copyto(sl[k], frames_left[li[b0 + k]].reshape(h, w * c)),
-                                     np.copyto(sr[k], frames_right[ri[b0 + k]].reshape(h, w * c))), range(cnt)))
-        st.submit(slot, cnt)
-        pending.append((slot, cnt))
-    while pending:
-        drain_one()
-    st.close()
-    for store in registered:
-        ctx.host_unregister(store)
-    if pool is not None:
-        pool.shutdown()
+        while pending:
+            drain_one()
+    finally:  # an exception must not leak the page-locked stores, the pinned ring or the copy threads
+        st.close()
+        for store in registered:
+            try:
+                ctx.host_unregister(store)
+            except api.UsvError:
+                pass
+        if pool is not None:
+            pool.shutdown()
     res = {"pair_left": li, "pair_right": ri, "dt": dt}
     for k, v in outs.items():
         res[k] = np.concatenate(v, axis=0) if v else np.zeros((0, 0), dtype=dict((n_, d) for n_, _, d in _abi.OUTPUT_FIELDS)[k])
