@@ -74,10 +74,33 @@ void IDMatcher(std::vector<Match> InterframeMatchIndexes, std::vector<Match> Old
                std::vector<cv::Point3i>& InterframeMatchIndexesComplete);
 
 // One call per frame pair in the reference's call order (P/Main.cpp:1115-1143, then the inline
-// disparity/distance of :681-694): generate -> resolve -> distance. Returns 0, or -1 on an
-// empty frame / GPU error like the reference's thread entry points (:908-911).
+// disparity/distance of :681-694): generate -> resolve -> distance, all three on the device
+// (usv_block_search_host). ExportMatches = exactly ResolveMatchList(per-window accepted winners), the
+// reference's TentativeMatch entry for entry; ExportDistances[k] = distance of ExportMatches[k].
+// Returns 0, or -1 on an empty frame / GPU error like the reference's thread entry points (:908-911).
 int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, const usv::ImageView* ImportGrayOtherCamera,
                 const BlockSearchSpec& Spec, std::vector<Match>& ExportMatches, std::vector<double>& ExportDistances);
+
+// Throughput form of the same path for a BATCH of independent frame pairs on one or more GPUs of the box (SURVEY 8e,
+// replacing the two free-running CameraThreads of P/Main.cpp:1407-1420 for recorded / synthetic streams): one host worker
+// thread per device, each with its own context, pinned ring and CUDA streams; pair p goes to device floor(p * G / N)
+// (contiguous blocks, no inter-GPU exchange); every worker lands its results in its own disjoint slice of the caller's
+// arrays. Per window: ResolvedDisparity = d of the window's winner if its record survives ResolveMatchList
+// (generate -> accept -> resolve all on the device), else 0xFFFF; RawCost (optional, SAD with 255 * n < 65536) = the
+// winner's integer cost. Distance = DistanceTable(...)[d]. Page-lock the frame and result arrays once with
+// BlockSearchPinHostBuffer for asynchronous copies (pageable memory works, slower).
+struct BlockSearchBatchStats {
+  double Seconds = 0.0;            // wall clock of the whole call (copies both ways included)
+  int DevicesUsed = 0;
+  long long PairsPerDevice[16] = {0};
+};
+int BlockSearchBatch(const unsigned char* LeftFrames, const unsigned char* RightFrames, int NumPairs, int Width, int Height, size_t Step,
+                     size_t FrameStep, const BlockSearchSpec& Spec, const std::vector<int>& Devices, unsigned short* ResolvedDisparity,
+                     unsigned short* RawCost = nullptr, BlockSearchBatchStats* Stats = nullptr);
+int BlockSearchPinHostBuffer(void* Buffer, size_t Bytes, int Device = 0);
+int BlockSearchUnpinHostBuffer(void* Buffer, int Device = 0);
+// distance[d], d = 0 .. Count - 1, for Spec.Distance (the table the kernels' epilogue reads)
+int DistanceTable(const BlockSearchSpec& Spec, int Count, std::vector<double>& Table);
 
 // The reference's per-frame pre-pass as one GPU call (P/Main.cpp:914-921): CalibrateLeft/RightImage (:351-359,
 // remap with the fixed-point maps initUndistortRectifyMap(..., CV_16SC2, ...) produces), cvtColor BGR2HSV,

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define USV_ABI_VERSION 2
+#define USV_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------ */
 #define USV_OK 0
@@ -118,6 +118,15 @@ typedef struct usv_outputs {
   uint16_t *raw_cost_u16;  /* raw_cost as u16 (0xFFFF = no candidate): SAD only,
                               and only when 255*tmpl_w*tmpl_h*channels fits 16
                               bits (else USV_ERR_UNSUPPORTED); lossless        */
+  uint16_t *resolved_disparity_u16;
+  /* Dense sweep only. The disparity map after ResolveMatchList (P/Main.cpp:432-477)
+   * has run over the pair's accepted winners ON THE DEVICE: entry = d of the window's
+   * winner if that record is (part of) the reference's TentativeMatch, i.e. no later
+   * window of the list claims the same RightIndex with a strictly smaller MatchValue
+   * (:450-451), else USV_NO_DISPARITY. With the W-entry distance table
+   * (usv_distance_lut) this is what the reference exports downstream — the distance of
+   * every surviving match (P/Main.cpp:1238-1259) — in 2 bytes per window. Rows of at
+   * most 2048 windows. */
 } usv_outputs;
 
 /* A context owns grow-only device scratch (staging buffers, distance LUTs,
@@ -198,6 +207,18 @@ int usv_match_templates_host(usv_ctx *ctx, const uint8_t *h_left,
                              const usv_outputs *h_out, uint32_t *h_cost_rows,
                              double *h_score_rows, int32_t row_cap);
 
+/* ---- generate -> resolve -> distance in ONE call, host buffers: the reference's call
+ * order for one frame pair (P/Main.cpp:1115-1143 then :681-694 / :1238). Dense sweep of
+ * the window grid (first minimum per window, accept test :417), the reference's
+ * whole-list ResolveMatchList (:432-477) over the accepted winners on the device, the
+ * distance of every surviving record. h_matches / h_distance receive the first `cap`
+ * records of TentativeMatch in the reference's order (duplicates and all); *n_out = its
+ * full length. h_distance may be NULL. Frames go through the context's pinned staging. */
+int usv_block_search_host(usv_ctx *ctx, const uint8_t *h_left,
+                          const uint8_t *h_right, const usv_frame_desc *frame,
+                          const usv_search_params *params, usv_match *h_matches,
+                          double *h_distance, int64_t cap, int64_t *n_out);
+
 /* ---- the reference's ORIGINAL cost: contour shape + size (P/Main.cpp:403-426) ----
  * cost(i, j) = cv::matchShapes(This[i], Other[j], CONTOURS_MATCH_I1, 0)
  *              + |area_i - area_j| / ((area_i + area_j) / 2)            (:413-415)
@@ -263,6 +284,12 @@ int usv_id_matcher(usv_ctx *ctx, const usv_match *h_cur, int64_t n_cur,
                    int64_t cap, int64_t *n_out);
 
 /* ---- distance family (host buffers; one tiny kernel each) ---------------- */
+/* The n-entry table distance[d], d = 0 .. n-1, built on the device by the function
+ * the matching kernels' epilogue evaluates (P/Main.cpp:694 or
+ * P/DistanceCalculator.cpp:84): consumers of the compact outputs (disparity_u16,
+ * resolved_disparity_u16) index it instead of moving 4 or 8 more bytes per window
+ * across PCIe. */
+int usv_distance_lut(usv_ctx *ctx, int32_t distance_kind, int32_t n, double *h_lut);
 int usv_disparity_to_distance(usv_ctx *ctx, const int32_t *h_disp, int64_t n,
                               int32_t distance_kind, double *h_dist);
 
@@ -313,6 +340,7 @@ int64_t usv_pair_nearest(const double *t_left, int64_t n_left,
 #define USV_OUT_DISTANCE_F32 0x20
 #define USV_OUT_DISPARITY_U16 0x40
 #define USV_OUT_RAW_COST_U16 0x80
+#define USV_OUT_RESOLVED_DISPARITY_U16 0x100
 
 int usv_stream_create(usv_ctx *ctx, const usv_frame_desc *frame,
                       const usv_search_params *params, int32_t pairs_per_slot,
@@ -345,6 +373,14 @@ int usv_stream_submit_gather(usv_stream *s, int32_t slot,
                              const int32_t *idx_right, int64_t n_store_frames,
                              const usv_frame_desc *store_frame,
                              int32_t n_pairs);
+/* Frames from, AND results into, the caller's own host memory: every output of
+ * the stream's mask is copied straight to the matching array of `h_dst` (entry 0 of
+ * each array = pair 0 of this submission) instead of the slot's pinned arrays — the
+ * way a multi-GPU worker lands its shard in a disjoint slice of one host result array
+ * (SURVEY 8e). Page-lock both sides (usv_host_register) for asynchronous copies. */
+int usv_stream_submit_io(usv_stream *s, int32_t slot, const uint8_t *h_left,
+                         const uint8_t *h_right, const usv_frame_desc *host_frame,
+                         int32_t n_pairs, const usv_outputs *h_dst);
 /* Page-lock / release a caller-owned host buffer (frame store, result array)
  * so that copies from / to it overlap with the kernels. */
 int usv_host_register(usv_ctx *ctx, void *p, size_t bytes);

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.Match) == 16 and _abi.Match.MatchValue.offset == 8
     assert C.sizeof(_abi.SearchParams) == 48 and _abi.SearchParams.accept_threshold.offset == 40
     assert C.sizeof(_abi.FrameDesc) == 24 and _abi.FrameDesc.frame_stride.offset == 16
-    assert C.sizeof(_abi.Outputs) == 64 and _abi.Outputs.raw_cost_u16.offset == 56
+    assert C.sizeof(_abi.Outputs) == 72 and _abi.Outputs.raw_cost_u16.offset == 56 and _abi.Outputs.resolved_disparity_u16.offset == 64
 
 
 def test_no_cpu_fallback():

@@ -415,3 +415,63 @@ def test_bounded_ranges_thin_last_pass(ctx, oracle, side, lo, n_disp):
     assert ctx.last_kernel == "dense_sad_argmin_kernel"
     for k in ("right_index", "raw_cost"):
         assert np.array_equal(got[k], exp[k]), k
+
+
+def _resolved_map_from_reference(oracle, got_pair, nx, use_ref):
+    """The reference's ResolveMatchList (restated, or its own lines compiled verbatim) over the accepted winners of one
+    pair -> the disparity map in which only the windows whose record is in TentativeMatch keep their disparity."""
+    win = got_pair["matches"]
+    kept = win[win["RightIndex"] != _abi.NO_MATCH]
+    out = (oracle.ref_resolve_match_list if use_ref else oracle.resolve_match_list)(kept)
+    alive = np.zeros(len(win), bool)
+    alive[np.unique(out["LeftIndex"])] = True
+    # every output record is one of the winners, unchanged
+    assert all(win[int(m["LeftIndex"])].tobytes() == m.tobytes() for m in out[:: max(1, len(out) // 200)])
+    return np.where(alive, got_pair["disparity_u16"], _abi.NO_DISPARITY).astype(np.uint16)
+
+
+@pytest.mark.parametrize("cost,side,w,h,tw,th,kw", [
+    ("sad", _abi.LEFT_CAM, 200, 40, 16, 16, dict()),
+    ("sad", _abi.RIGHT_CAM, 131, 30, 8, 8, dict(search_max=40)),
+    ("ssd", _abi.LEFT_CAM, 150, 28, 12, 12, dict(search_min=2, search_max=60, accept_threshold=0.05)),
+    ("zncc", _abi.LEFT_CAM, 160, 30, 16, 16, dict(search_max=63)),
+    ("ncc", _abi.RIGHT_CAM, 140, 26, 9, 7, dict(search_max=50, accept_threshold=0.3)),
+    ("sad", _abi.LEFT_CAM, 96, 24, 11, 4, dict(stride_x=2, stride_y=3, search_max=40)),   # direct-form kernel
+])
+def test_resolved_disparity_map(ctx, oracle, cost, side, w, h, tw, th, kw):
+    """usv_outputs.resolved_disparity_u16: ResolveMatchList (P/Main.cpp:432-477) over the dense winners on the device. Frames with
+    flat and repeated regions, so that many windows claim the same RightIndex with equal and with different values."""
+    left, right = synth.make_pairs(2, w, h, 1, shift=9 if side == _abi.LEFT_CAM else -9, noise_sigma=2.0, seed=w + h)
+    left[0, :, w // 2:] = 77                      # flat half: all-tie rows of candidates
+    right[0, :, : w // 3] = right[0, :, w // 3: 2 * (w // 3)]  # repeated texture: two windows, one best x'
+    right[1] = np.roll(right[1], 1, axis=0) // 2
+    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost=cost, camera_side=side, **kw)
+    full = api.ALL_OUTPUTS | _abi.OUT_RESOLVED_DISPARITY_U16
+    got = ctx.match_dense(left, right, p, mask=full)
+    f = _abi.frame_desc_for(left)
+    nx, ny, _ = api.grid_dims(f, p)
+    n_beaten = 0
+    for pair in range(2):
+        gp = {k: v[pair] for k, v in got.items()}
+        exp = _resolved_map_from_reference(oracle, gp, nx, use_ref=(pair == 0))
+        assert np.array_equal(gp["resolved_disparity_u16"], exp)
+        n_beaten += int(((exp == _abi.NO_DISPARITY) & (gp["disparity_u16"] != _abi.NO_DISPARITY)).sum())
+    assert n_beaten > 0  # the case exercises the conflict rule
+    # the same map when the winners come from right_index + raw_cost, and from the library's own scratch
+    for mask in (_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST | _abi.OUT_RESOLVED_DISPARITY_U16, _abi.OUT_RESOLVED_DISPARITY_U16):
+        again = ctx.match_dense(left, right, p, mask=mask)
+        assert np.array_equal(again["resolved_disparity_u16"], got["resolved_disparity_u16"])
+
+
+def test_distance_lut_matches_epilogue(ctx, oracle):
+    for kind in (_abi.DIST_PINHOLE, _abi.DIST_POWERLAW):
+        lut = ctx.distance_lut(kind, 700)
+        exp = oracle.distance(np.arange(700), kind)
+        assert np.array_equal(np.isinf(lut), np.isinf(exp))
+        fin = np.isfinite(exp)
+        assert np.allclose(lut[fin], exp[fin], rtol=DIST_RTOL, atol=0)
+    left, right = synth.make_pairs(1, 128, 24, 1, shift=7, noise_sigma=1.0, seed=3)
+    got = ctx.match_dense(left, right, _abi.make_params(tmpl_w=8, tmpl_h=8, cost="sad"))
+    d = got["disparity_u16"][0]
+    ok = d != _abi.NO_DISPARITY
+    assert np.array_equal(got["distance"][0][ok], ctx.distance_lut(_abi.DIST_PINHOLE, 128)[d[ok]])  # same table, bit for bit

@@ -96,12 +96,14 @@ def test_host_binary_against_oracle(oracle):
     matches = np.frombuffer(raw, _abi.MATCH_DTYPE, n_m, off); off += 16 * n_m
     dist = np.frombuffer(raw, np.float64, n_m, off); off += 8 * n_m
     allc = np.frombuffer(raw, _abi.MATCH_DTYPE, n_all, off)
-    # dense: BlockSearch == oracle's accepted per-window winners, in window order
+    # dense: BlockSearch == the reference's ResolveMatchList (restated, pinned to the reference's own lines) over the oracle's
+    # accepted per-window winners, entry for entry, with the distance of every entry
     p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad")
     exp = oracle.match_dense(L, R, p)
     keep = exp["right_index"][0] != _abi.NO_MATCH
-    assert matches.tobytes() == exp["matches"][0][keep].tobytes()
-    assert np.allclose(dist, exp["distance"][0][keep], rtol=1e-12, atol=0)
+    exp_list = oracle.resolve_match_list(exp["matches"][0][keep])
+    assert matches.tobytes() == exp_list.tobytes()
+    assert np.allclose(dist, exp["distance"][0][exp_list["LeftIndex"]], rtol=1e-12, atol=0)
     # templates: every accepted candidate, i-major / j-minor, ZNCC cost = 1 - score
     pz = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="zncc")
     rows = oracle.match_templates(L, R, [300, 400], [20, 30], pz, rows=True)["score_rows"][0]

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-USV_ABI_VERSION = 2
+USV_ABI_VERSION = 3
 USV_OK, USV_ERR_INVALID_ARG, USV_ERR_CUDA, USV_ERR_NO_DEVICE, USV_ERR_UNSUPPORTED, USV_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 COST_SAD, COST_SSD, COST_NCC, COST_ZNCC = 0, 1, 2, 3
 COST_NAMES = {"sad": COST_SAD, "ssd": COST_SSD, "ncc": COST_NCC, "zncc": COST_ZNCC}
@@ -14,6 +14,7 @@ NO_DISPARITY = 0xFFFF
 
 OUT_MATCHES, OUT_RIGHT_INDEX, OUT_RAW_COST, OUT_SCORE = 0x01, 0x02, 0x04, 0x08
 OUT_DISTANCE, OUT_DISTANCE_F32, OUT_DISPARITY_U16, OUT_RAW_COST_U16 = 0x10, 0x20, 0x40, 0x80
+OUT_RESOLVED_DISPARITY_U16 = 0x100
 
 # numpy view of the reference's 16-byte `class Match` (P/Match.hpp:4-12)
 MATCH_DTYPE = np.dtype([("LeftIndex", "<u4"), ("RightIndex", "<u4"), ("MatchValue", "<f8")], align=True)
@@ -56,7 +57,7 @@ class Outputs(C.Structure):
     _fields_ = [
         ("matches", C.c_void_p), ("right_index", C.c_void_p), ("raw_cost", C.c_void_p),
         ("score", C.c_void_p), ("distance", C.c_void_p), ("distance_f32", C.c_void_p),
-        ("disparity_u16", C.c_void_p), ("raw_cost_u16", C.c_void_p),
+        ("disparity_u16", C.c_void_p), ("raw_cost_u16", C.c_void_p), ("resolved_disparity_u16", C.c_void_p),
     ]
 
 
@@ -70,6 +71,7 @@ OUTPUT_FIELDS = (
     ("distance_f32", OUT_DISTANCE_F32, np.dtype("<f4")),
     ("disparity_u16", OUT_DISPARITY_U16, np.dtype("<u2")),
     ("raw_cost_u16", OUT_RAW_COST_U16, np.dtype("<u2")),
+    ("resolved_disparity_u16", OUT_RESOLVED_DISPARITY_U16, np.dtype("<u2")),
 )
 
 

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libusv_b200.so")
 
 # every symbol include/usv_b200.h declares
 EXPORTS = (
-    "usv_abi_version", "usv_create", "usv_destroy", "usv_last_error", "usv_launch_count", "usv_last_kernel", "usv_device_status", "usv_set_option",
+    "usv_abi_version", "usv_create", "usv_destroy", "usv_last_error", "usv_launch_count", "usv_last_kernel", "usv_device_status", "usv_set_option", "usv_distance_lut", "usv_block_search_host", "usv_stream_submit_io",
     "usv_grid_dims", "usv_match_dense_device", "usv_match_dense_host", "usv_match_templates_device",
     "usv_match_templates_host", "usv_disparity_to_distance", "usv_moving_object_distance",
     "usv_coordinate_position", "usv_pair_nearest", "usv_stream_create", "usv_stream_destroy",
@@ -205,6 +205,12 @@ class Context:
         out = np.zeros(d.shape, np.float64)
         self._check(lib().usv_disparity_to_distance(self._h, _ptr(d), C.c_int64(d.size), C.c_int32(kind), _ptr(out)),
                     "usv_disparity_to_distance")
+        return out
+
+    def distance_lut(self, kind, n):
+        """distance[d] for d = 0 .. n-1, built on the device by the kernels' own epilogue function."""
+        out = np.zeros(int(n), np.float64)
+        self._check(lib().usv_distance_lut(self._h, C.c_int32(int(kind)), C.c_int32(int(n)), _ptr(out)), "usv_distance_lut")
         return out
 
     def moving_object_distance(self, camera_side, t_this, this_xy, other_xy, old_xy, older_xy, idx3, t_other, t_old, t_older):

@@ -3,8 +3,12 @@
 // dumped candidate costs (template overload) and forwards ResolveMatchList to the GPU resolve.
 #include "../../../include/SearchAlgorithms.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <thread>
 
 #include "usv_host_ctx.hpp"
 
@@ -72,18 +76,27 @@ void GenerateMatchingList(const usv::ImageView& ThisCamera, const usv::ImageView
   int32_t nx = 0, ny = 0;
   if (usv_grid_dims(&f, &p, &nx, &ny, nullptr) != USV_OK) { tc.last_error = "GenerateMatchingList: template does not fit the frame"; return; }
   const size_t n = (size_t)nx * ny;
-  std::vector<usv_match> rec(n);
-  std::vector<double> dist(Distances ? n : 0);
+  // thread-local result buffers, reused from call to call (no 4.6 MB allocation + page faults per frame pair)
+  static thread_local std::vector<usv_match> rec;
+  static thread_local std::vector<double> dist;
+  if (rec.size() < n) rec.resize(n);
+  if (Distances && dist.size() < n) dist.resize(n);
   usv_outputs out;
   std::memset(&out, 0, sizeof(out));
   out.matches = rec.data();
   if (Distances) out.distance = dist.data();
   const int rc = usv_match_dense_host(ctx, ThisCamera.data, OtherCamera.data, &f, 1, &p, &out);
   if (!tc.check(ctx, rc, "usv_match_dense_host")) return;
-  for (size_t i = 0; i < n; ++i) {
-    if (rec[i].RightIndex == USV_NO_MATCH) continue;  // no candidate passed `< AcceptThreshold` (P/Main.cpp:417)
-    Matcher.push_back({rec[i].LeftIndex, rec[i].RightIndex, rec[i].MatchValue});
-    if (Distances) Distances->push_back(dist[i]);
+  static_assert(sizeof(Match) == sizeof(usv_match), "Match must stay bit-identical to usv_match");
+  const Match* as_match = reinterpret_cast<const Match*>(rec.data());
+  // runs of accepted windows are appended in bulk (usually the whole list is one run)
+  for (size_t i = 0; i < n;) {
+    if (rec[i].RightIndex == USV_NO_MATCH) { ++i; continue; }  // no candidate passed `< AcceptThreshold` (P/Main.cpp:417)
+    size_t j = i + 1;
+    while (j < n && rec[j].RightIndex != USV_NO_MATCH) ++j;
+    Matcher.insert(Matcher.end(), as_match + i, as_match + j);
+    if (Distances) Distances->insert(Distances->end(), dist.begin() + i, dist.begin() + j);
+    i = j;
   }
 }
 
@@ -194,7 +207,154 @@ int BlockSearch(bool CameraSide, const usv::ImageView* ImportGrayThisCamera, con
   s.CameraSide = CameraSide;
   ExportMatches.clear();
   ExportDistances.clear();
-  // generate + per-window resolve are one fused kernel; the distance is its epilogue
-  GenerateMatchingList(*ImportGrayThisCamera, *ImportGrayOtherCamera, s, ExportMatches, &ExportDistances);
-  return usv::thread_contexts().last_error.empty() ? 0 : -1;
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  if (!same_geometry(*ImportGrayThisCamera, *ImportGrayOtherCamera)) { tc.last_error = "BlockSearch: frames of different geometry"; return -1; }
+  usv_ctx* ctx = tc.get(s.Device);
+  if (!ctx) return -1;
+  const usv_search_params p = to_params(s);
+  const usv_frame_desc f = to_frame(*ImportGrayThisCamera);
+  int32_t nx = 0, ny = 0;
+  if (usv_grid_dims(&f, &p, &nx, &ny, nullptr) != USV_OK) { tc.last_error = "BlockSearch: template does not fit the frame"; return -1; }
+  const size_t n = (size_t)nx * ny;
+  // generate -> resolve -> distance on the device; the survivors land in thread-local buffers and are appended in bulk
+  static thread_local std::vector<usv_match> rec;
+  static thread_local std::vector<double> dist;
+  if (rec.size() < n) { rec.resize(n); dist.resize(n); }
+  int64_t n_out = 0;
+  const int rc = usv_block_search_host(ctx, ImportGrayThisCamera->data, ImportGrayOtherCamera->data, &f, &p, rec.data(), dist.data(), (int64_t)n, &n_out);
+  if (!tc.check(ctx, rc, "usv_block_search_host")) return -1;
+  const Match* as_match = reinterpret_cast<const Match*>(rec.data());
+  ExportMatches.assign(as_match, as_match + n_out);
+  ExportDistances.assign(dist.begin(), dist.begin() + n_out);
+  return 0;
+}
+
+int BlockSearchPinHostBuffer(void* Buffer, size_t Bytes, int Device) {
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  usv_ctx* ctx = tc.get(Device);
+  if (!ctx) return -1;
+  return tc.check(ctx, usv_host_register(ctx, Buffer, Bytes), "usv_host_register") ? 0 : -1;
+}
+
+int BlockSearchUnpinHostBuffer(void* Buffer, int Device) {
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  usv_ctx* ctx = tc.get(Device);
+  if (!ctx) return -1;
+  return tc.check(ctx, usv_host_unregister(ctx, Buffer), "usv_host_unregister") ? 0 : -1;
+}
+
+int DistanceTable(const BlockSearchSpec& Spec, int Count, std::vector<double>& Table) {
+  usv::ThreadContexts& tc = usv::thread_contexts();
+  usv_ctx* ctx = tc.get(Spec.Device);
+  if (!ctx || Count <= 0) return -1;
+  Table.assign((size_t)Count, 0.0);
+  if (Spec.Distance == BlockSearchSpec::NoDistance) return 0;
+  return tc.check(ctx, usv_distance_lut(ctx, (int)Spec.Distance, Count, Table.data()), "usv_distance_lut") ? 0 : -1;
+}
+
+namespace {
+struct BatchWorker {
+  std::mutex busy;
+  usv_ctx* ctx = nullptr;
+  usv_stream* st = nullptr;
+  usv_frame_desc f;
+  usv_search_params p;
+  uint32_t mask = 0;
+  int pps = 0, n_slots = 0;
+};
+// never destroyed: the CUDA runtime may already be gone when static destructors run
+BatchWorker& batch_worker(int device) {
+  static std::mutex m;
+  static std::map<int, BatchWorker*>* all = new std::map<int, BatchWorker*>();
+  std::lock_guard<std::mutex> lock(m);
+  BatchWorker*& w = (*all)[device];
+  if (!w) w = new BatchWorker();
+  return *w;
+}
+}  // namespace
+
+// One worker per device: context + pinned ring (usv_stream) + one CUDA stream per slot. The worker feeds its contiguous
+// block of pairs through the ring, frames straight from the caller's arrays, results straight into its slice of the
+// caller's arrays (usv_stream_submit_io): no host-side copy, no shared state between workers, no inter-GPU exchange.
+int BlockSearchBatch(const unsigned char* LeftFrames, const unsigned char* RightFrames, int NumPairs, int Width, int Height, size_t Step,
+                     size_t FrameStep, const BlockSearchSpec& Spec, const std::vector<int>& Devices, unsigned short* ResolvedDisparity,
+                     unsigned short* RawCost, BlockSearchBatchStats* Stats) {
+  usv::ThreadContexts& tc0 = usv::thread_contexts();
+  if (!LeftFrames || !RightFrames || !ResolvedDisparity || NumPairs < 0 || Devices.empty() || Devices.size() > 16) {
+    tc0.last_error = "BlockSearchBatch: bad arguments";
+    return -1;
+  }
+  const usv_search_params p = to_params(Spec);
+  usv_frame_desc f;
+  f.width = Width; f.height = Height; f.channels = 1;
+  f.row_stride = (int32_t)Step; f.frame_stride = (int64_t)FrameStep;
+  int32_t nx = 0, ny = 0;
+  if (usv_grid_dims(&f, &p, &nx, &ny, nullptr) != USV_OK) { tc0.last_error = "BlockSearchBatch: template does not fit the frame"; return -1; }
+  const size_t n_win = (size_t)nx * ny;
+  const int G = (int)Devices.size();
+  std::vector<std::string> errors(G);
+  std::vector<long long> done(G, 0);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&](int g) {
+    // pair p -> device floor(p * G / N): contiguous blocks
+    const long long lo = ((long long)g * NumPairs + G - 1) / G, hi = ((long long)(g + 1) * NumPairs + G - 1) / G;
+    if (hi <= lo) return;
+    // the device's worker state (context, pinned ring, streams) outlives the call: the next batch of the same geometry
+    // starts without a single allocation
+    BatchWorker& bw = batch_worker(Devices[g]);
+    std::lock_guard<std::mutex> lock(bw.busy);
+    if (!bw.ctx && usv_create(Devices[g], &bw.ctx) != USV_OK) {
+      bw.ctx = nullptr;
+      errors[g] = "usv_create failed: no usable sm_100 CUDA device; there is no CPU fallback";
+      return;
+    }
+    usv_ctx* ctx = bw.ctx;
+    const int pps = (int)std::min<long long>(32, hi - lo), n_slots = (int)std::min<long long>(6, (hi - lo + pps - 1) / pps);
+    const uint32_t mask = USV_OUT_RESOLVED_DISPARITY_U16 | (RawCost ? USV_OUT_RAW_COST_U16 : 0u);
+    int rc = USV_OK;
+    if (!bw.st || std::memcmp(&bw.f, &f, sizeof(f)) || std::memcmp(&bw.p, &p, sizeof(p)) || bw.mask != mask || bw.pps < pps || bw.n_slots < n_slots) {
+      if (bw.st) usv_stream_destroy(bw.st);
+      bw.st = nullptr;
+      rc = usv_stream_create(ctx, &f, &p, pps, n_slots, mask, &bw.st);
+      if (rc != USV_OK) { bw.st = nullptr; errors[g] = std::string("usv_stream_create: ") + usv_last_error(ctx); return; }
+      bw.f = f; bw.p = p; bw.mask = mask; bw.pps = pps; bw.n_slots = n_slots;
+    }
+    usv_stream* st = bw.st;
+    long long submitted = lo, waited = lo;
+    int slot_sub = 0, slot_wait = 0, in_flight = 0;
+    while (waited < hi && rc == USV_OK) {
+      if (submitted < hi && in_flight < n_slots) {
+        const int cnt = (int)std::min<long long>(pps, hi - submitted);
+        usv_outputs dst;
+        std::memset(&dst, 0, sizeof(dst));
+        dst.resolved_disparity_u16 = ResolvedDisparity + (size_t)submitted * n_win;
+        if (RawCost) dst.raw_cost_u16 = RawCost + (size_t)submitted * n_win;
+        rc = usv_stream_submit_io(st, slot_sub, LeftFrames + (size_t)submitted * FrameStep, RightFrames + (size_t)submitted * FrameStep, &f,
+                                  cnt, &dst);
+        submitted += cnt;
+        slot_sub = (slot_sub + 1) % n_slots;
+        ++in_flight;
+      } else {
+        rc = usv_stream_wait(st, slot_wait);
+        waited = std::min<long long>(hi, waited + pps);
+        slot_wait = (slot_wait + 1) % n_slots;
+        --in_flight;
+      }
+    }
+    if (rc != USV_OK) errors[g] = std::string("stream: ") + usv_last_error(ctx);
+    done[g] = waited - lo;
+  };
+  std::vector<std::thread> threads;
+  for (int g = 1; g < G; ++g) threads.emplace_back(worker, g);
+  worker(0);  // the calling thread is the first worker
+  for (auto& t : threads) t.join();
+  if (Stats) {
+    Stats->Seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    Stats->DevicesUsed = G;
+    for (int g = 0; g < G; ++g) Stats->PairsPerDevice[g] = done[g];
+  }
+  for (int g = 0; g < G; ++g)
+    if (!errors[g].empty()) { tc0.last_error = "BlockSearchBatch, device " + std::to_string(Devices[g]) + ": " + errors[g]; return -1; }
+  tc0.last_error.clear();
+  return 0;
 }

@@ -3,6 +3,8 @@
 // :1238-1247), checks the reference's known answers and dumps the frames
 // and results so that tests/test_host_cpp.py can compare them with the CPU oracle.
 //   usv_host_test <dump-file>
+//   usv_host_test --bench <pairs> <n_devices> <steps> <warmup>     (one JSON line: the C++ drop-in's throughput)
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +22,77 @@ static int fails = 0;
 
 static bool close_rel(double a, double b, double rel) { return std::fabs(a - b) <= rel * std::fabs(b); }
 
+// Throughput of the C++ layer on the bench workload (640x480 gray, 16x16 SAD, full range): BlockSearchBatch over
+// n_dev GPUs (one worker thread + context + pinned ring per GPU, results into disjoint slices of one pinned host
+// array) and the per-pair BlockSearch call of the reference's call sites. Host buffers, copies both ways timed.
+static int run_bench(int pairs, int n_dev, int steps, int warmup) {
+  const int W = 640, H = 480;
+  const size_t fsz = (size_t)W * H;
+  std::vector<uint8_t> L(fsz * pairs), R(fsz * pairs);
+  uint32_t s = 325u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (uint8_t)(s >> 24); };
+  for (int p = 0; p < pairs; ++p) {
+    uint8_t* l = L.data() + fsz * p;
+    uint8_t* r = R.data() + fsz * p;
+    for (size_t k = 0; k < fsz; ++k) l[k] = rnd();
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) r[(size_t)y * W + x] = x + 37 < W ? l[(size_t)y * W + x + 37] : rnd();
+  }
+  BlockSearchSpec spec;
+  const size_t n_win = (size_t)(W - 15) * (H - 15);
+  std::vector<unsigned short> disp(n_win * pairs), cost(n_win * pairs);
+  std::vector<int> devices;
+  for (int g = 0; g < n_dev; ++g) devices.push_back(g);
+  if (BlockSearchPinHostBuffer(L.data(), L.size()) || BlockSearchPinHostBuffer(R.data(), R.size()) ||
+      BlockSearchPinHostBuffer(disp.data(), disp.size() * 2) || BlockSearchPinHostBuffer(cost.data(), cost.size() * 2)) {
+    std::printf("{\"error\": \"%s\"}\n", BlockSearchLastError());
+    return 2;
+  }
+  BlockSearchBatchStats st;
+  auto run = [&](unsigned short* cost_out) { return BlockSearchBatch(L.data(), R.data(), pairs, W, H, W, fsz, spec, devices, disp.data(), cost_out, &st); };
+  double t_disp = 0.0, t_both = 0.0;
+  for (int variant = 0; variant < 2; ++variant) {
+    unsigned short* co = variant ? cost.data() : nullptr;
+    for (int k = 0; k < warmup; ++k)
+      if (run(co)) { std::printf("{\"error\": \"%s\"}\n", BlockSearchLastError()); return 2; }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int k = 0; k < steps; ++k) run(co);
+    (variant ? t_both : t_disp) = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  // sanity of the timed output: the known shift is recovered, at cost 0
+  size_t good = 0, seen = 0;
+  for (int p = 0; p < pairs; p += std::max(1, pairs / 4))
+    for (int y = 0; y < H - 15; y += 29)
+      for (int x = 37; x < W - 15; x += 7) { ++seen; good += disp[(size_t)p * n_win + (size_t)y * (W - 15) + x] == 37 && cost[(size_t)p * n_win + (size_t)y * (W - 15) + x] == 0; }
+  // the reference-shaped per-pair call (generate -> resolve -> distance, vectors out)
+  usv::ImageView left(L.data(), W, H, 1, W), right(R.data(), W, H, 1, W);
+  std::vector<Match> m;
+  std::vector<double> d;
+  int n_single = 0;
+  for (int k = 0; k < 3; ++k) BlockSearch(LeftCam, &left, &right, spec, m, d);
+  const auto t1 = std::chrono::steady_clock::now();
+  double t_single = 0.0;
+  while (t_single < 1.0) {
+    usv::ImageView l2(L.data() + fsz * (n_single % pairs), W, H, 1, W), r2(R.data() + fsz * (n_single % pairs), W, H, 1, W);
+    BlockSearch(LeftCam, &l2, &r2, spec, m, d);
+    ++n_single;
+    t_single = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+  }
+  std::printf("{\"api\": \"BlockSearchBatch (C++), one worker thread + context + pinned ring per GPU, frames from and results into the caller's "
+              "page-locked arrays\", \"pairs\": %d, \"n_devices\": %d, \"steps\": %d, \"pairs_per_s\": %.1f, \"outputs\": \"resolved_disparity_u16 (2 B/window)\", "
+              "\"with_cost\": {\"pairs_per_s\": %.1f, \"outputs\": \"resolved_disparity_u16 + raw_cost_u16 (4 B/window)\"}, "
+              "\"known_shift_recovered\": %s, \"block_search_single_pair\": {\"api\": \"BlockSearch (generate -> resolve -> distance, std::vector<Match> out), one "
+              "host thread\", \"pairs_per_s\": %.1f, \"matches_per_pair\": %zu}}\n",
+              pairs, n_dev, steps, (double)pairs * steps / t_disp, (double)pairs * steps / t_both, good == seen ? "true" : "false", n_single / t_single, m.size());
+  BlockSearchUnpinHostBuffer(L.data());
+  BlockSearchUnpinHostBuffer(R.data());
+  BlockSearchUnpinHostBuffer(disp.data());
+  BlockSearchUnpinHostBuffer(cost.data());
+  return good == seen ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 6 && std::strcmp(argv[1], "--bench") == 0) return run_bench(std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5]));
   // ---- Match: the reference's record
   static_assert(sizeof(Match) == 16, "Match layout");
   Match m0(1, 2, 0.5);
@@ -81,13 +153,30 @@ int main(int argc, char** argv) {
   if (rc != 0) { std::printf("BlockSearch failed: %s\n", BlockSearchLastError()); return 2; }
   const int nxc = W - 16 + 1, nyc = H - 16 + 1;
   CHECK(matches.size() == dist.size() && !matches.empty());
+  // BlockSearch = ResolveMatchList over the accepted per-window winners: a window with an exact counterpart (cost 0) is never
+  // strictly beaten, so every such window is in the list (possibly more than once: the reference keeps duplicates)
+  std::vector<char> seen_exact((size_t)nxc * nyc, 0);
   size_t exact = 0;
   for (size_t k = 0; k < matches.size(); ++k) {
     const int x = matches[k].LeftIndex % nxc, y = matches[k].LeftIndex / nxc, xr = matches[k].RightIndex - y * nxc;
-    if (x >= SHIFT) { CHECK(x - xr == SHIFT && matches[k].MatchValue == 0.0); ++exact; }
+    if (x >= SHIFT) { CHECK(x - xr == SHIFT && matches[k].MatchValue == 0.0); if (!seen_exact[matches[k].LeftIndex]) { seen_exact[matches[k].LeftIndex] = 1; ++exact; } }
     CHECK(close_rel(dist[k], ((201.6 * 4) / ((x - xr) * 0.000043)) / 1000, 1e-12) || x == xr);
   }
   CHECK(exact == (size_t)(nxc - SHIFT) * nyc);
+  // the batch form over the same pair: the resolved disparity map marks exactly the windows that appear in the list
+  {
+    std::vector<unsigned short> rd((size_t)nxc * nyc), rc16((size_t)nxc * nyc);
+    BlockSearchBatchStats bs;
+    CHECK(BlockSearchBatch(L.data(), R.data(), 1, W, H, W, (size_t)W * H, spec, std::vector<int>{0}, rd.data(), rc16.data(), &bs) == 0);
+    std::vector<char> in_list((size_t)nxc * nyc, 0);
+    for (const Match& m : matches) in_list[m.LeftIndex] = 1;
+    size_t bad = 0;
+    for (size_t w = 0; w < rd.size(); ++w) bad += (rd[w] != 0xFFFF) != (in_list[w] != 0);
+    CHECK(bad == 0 && bs.DevicesUsed == 1 && bs.PairsPerDevice[0] == 1);
+    std::vector<double> table;
+    CHECK(DistanceTable(spec, W, table) == 0 && table.size() == (size_t)W);
+    for (size_t k = 0; k < matches.size(); k += 97) CHECK(table[rd[matches[k].LeftIndex]] == dist[k]);
+  }
   CHECK(BlockSearch(LeftCam, nullptr, &right, spec, matches, dist) == -1);  // empty frame -> -1 (P/Main.cpp:908-911)
   rc = BlockSearch(LeftCam, &left, &right, spec, matches, dist);
   CHECK(rc == 0);

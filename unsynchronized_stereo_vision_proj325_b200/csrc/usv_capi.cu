@@ -27,6 +27,9 @@ size_t resolve_workspace_bytes(long long n);
 cudaError_t launch_resolve(const usv_match* d_in, long long n, int skip_unmatched, usv_match* d_out, long long cap, long long* d_n_out,
                            void* d_ws, size_t ws_bytes, cudaStream_t st, int* n_launches);
 size_t id_matcher_workspace_bytes(long long n_cur);
+bool resolve_rows_supported(int nx, int nxc);
+cudaError_t launch_resolve_rows(const uint32_t* d_right_index, const uint32_t* d_raw_cost, const usv_match* d_matches, int nx, int ny, int sx,
+                                int nxc, long long n_templates, int camera_side, int n_pairs, uint16_t* d_out, cudaStream_t st);
 cudaError_t launch_id_matcher(const usv_match* d_cur, long long n_cur, const usv_match* d_old, long long n_old, int* d_out3,
                               long long cap, long long* d_n_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
 size_t preprocess_scratch_bytes(int width, int height, int n_frames);
@@ -36,6 +39,8 @@ cudaError_t launch_preprocess(int device, const uint8_t* d_src, uint8_t* d_dst, 
 cudaError_t run_issue_probe(int which, int sms, double target_ms, double* lane_inst_per_s, uint32_t* d_scratch, cudaStream_t st);
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st);
 cudaError_t launch_build_distance_lut(double* d_lut, int n, int kind, cudaStream_t st);
+cudaError_t launch_match_list_distance(const usv_match* d_list, const long long* d_n, long long cap, int nx, int sx, int nxc, int camera_side,
+                                       int kind, const double* lut, int lut_n, double* d_out, cudaStream_t st);
 cudaError_t launch_moving_object_distance(int camera_side, long long t_this, const float* this_xy, int n_this, const float* other_xy,
                                           int n_other, const float* old_xy, int n_old, const float* older_xy, int n_older,
                                           const int* idx3, int n_idx, long long t_other, long long t_old, long long t_older,
@@ -68,13 +73,16 @@ struct usv_ctx {
   int* d_status = nullptr;
   int sm_count = 148;
   int corr_kernel = USV_CORR_KERNEL_AUTO;
-  std::atomic<int> open_streams{0};  // usv_destroy refuses while a usv_stream of this context is alive
+  std::atomic<int> open_streams{0};
+  // grow-only pinned staging of usv_block_search_host (frames in, match list + distances out)
+  void* pin[3] = {nullptr, nullptr, nullptr};
+  size_t pin_cap[3] = {0, 0, 0};  // usv_destroy refuses while a usv_stream of this context is alive
   // grow-only scratch for the host paths
-  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[8], misc[8], resolve_ws, pre_ws, corr_ws;
+  DevBuf in_l, in_r, tx, ty, rows_u32, rows_f64, out[9], misc[8], resolve_ws, pre_ws, corr_ws, win_ws;
 };
 
-static const int kNumOut = 8;
-static const size_t kOutElem[kNumOut] = {sizeof(usv_match), 4, 4, 8, 8, 4, 2, 2};
+static const int kNumOut = 9;
+static const size_t kOutElem[kNumOut] = {sizeof(usv_match), 4, 4, 8, 8, 4, 2, 2, 2};
 
 static int fail(usv_ctx* c, int code, const char* fmt, ...) {
   if (c) {
@@ -111,7 +119,8 @@ static void** out_slot(usv_outputs* o, int i) {
     case 4: return (void**)&o->distance;
     case 5: return (void**)&o->distance_f32;
     case 6: return (void**)&o->disparity_u16;
-    default: return (void**)&o->raw_cost_u16;
+    case 7: return (void**)&o->raw_cost_u16;
+    default: return (void**)&o->resolved_disparity_u16;
   }
 }
 
@@ -244,9 +253,11 @@ extern "C" int usv_destroy(usv_ctx* ctx) {
   if (ctx->resolve_ws.p) cudaFree(ctx->resolve_ws.p);
   if (ctx->pre_ws.p) cudaFree(ctx->pre_ws.p);
   if (ctx->corr_ws.p) cudaFree(ctx->corr_ws.p);
+  if (ctx->win_ws.p) cudaFree(ctx->win_ws.p);
   for (double* l : ctx->lut) if (l) cudaFree(l);
   for (void* l : ctx->retired) cudaFree(l);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  for (void* q : ctx->pin) if (q) cudaFreeHost(q);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return USV_OK;
@@ -283,32 +294,13 @@ extern "C" int usv_grid_dims(const usv_frame_desc* f, const usv_search_params* p
   return USV_OK;
 }
 
+static int resolve_device(usv_ctx* ctx, const usv_match* d_in, int64_t n, int32_t skip_unmatched, usv_match* d_out, int64_t cap,
+                          int64_t* d_n_out, cudaStream_t st);
+
 // ---- matching: device pointers -----------------------------------------------------
-static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, const usv_frame_desc* f, int32_t n_pairs,
-                        const usv_search_params* p, const usv_outputs* d_out, const int32_t* d_tx, const int32_t* d_ty,
-                        int32_t n_templates, uint32_t* d_cost_rows, double* d_score_rows, int32_t row_cap, cudaStream_t st, DevBuf* corr_ws = nullptr) {
-  int rc = check_common(ctx, f, p, n_pairs);
-  if (rc) return rc;
-  if (!d_left || !d_right || !d_out) return fail(ctx, USV_ERR_INVALID_ARG, "null device pointer");
-  if (!aligned16(d_left) || !aligned16(d_right) || (f->row_stride & 15) || (f->frame_stride & 15))
-    return fail(ctx, USV_ERR_INVALID_ARG, "device frames need 16-byte aligned base, row_stride and frame_stride");
-  if (d_out->raw_cost_u16 && (rc = check_cost_u16(ctx, f, p))) return rc;
-  if (n_pairs == 0) return USV_OK;
-  CU(cudaSetDevice(ctx->device));
-  DevJob J;
-  fill_job(ctx, J, d_left, d_right, f, p, d_out);
-  const bool sparse = d_tx != nullptr;
-  if (sparse) {
-    if (!d_ty || n_templates < 0) return fail(ctx, USV_ERR_INVALID_ARG, "bad template list");
-    if (n_templates == 0) return USV_OK;
-    J.tx = d_tx; J.ty = d_ty; J.n_templates = n_templates;
-    J.cost_rows = d_cost_rows; J.score_rows = d_score_rows; J.row_cap = row_cap;
-    if ((d_cost_rows || d_score_rows) && row_cap <= 0) return fail(ctx, USV_ERR_INVALID_ARG, "row_cap must be positive");
-  }
-  if (J.out.distance || J.out.distance_f32) {
-    rc = ensure_lut(ctx, p->distance_kind, f->width, st, &J.dist_lut);
-    if (rc) return rc;
-  }
+// the matching kernels of one call (dense sweeps first, the direct form for everything they do not cover)
+static int dispatch_match(usv_ctx* ctx, const DevJob& J, int32_t n_pairs, bool sparse, cudaStream_t st, DevBuf* corr_ws) {
+  int rc;
   if (!sparse) {
     const char* name = nullptr;
     int nl = 0;
@@ -343,6 +335,64 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
   if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "direct launch: %s", cudaGetErrorString(e));
   ctx->launches++;
   ctx->last_kernel = "block_cost_argmin_direct";
+  return USV_OK;
+}
+
+static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, const usv_frame_desc* f, int32_t n_pairs,
+                        const usv_search_params* p, const usv_outputs* d_out, const int32_t* d_tx, const int32_t* d_ty,
+                        int32_t n_templates, uint32_t* d_cost_rows, double* d_score_rows, int32_t row_cap, cudaStream_t st, DevBuf* corr_ws = nullptr,
+                        DevBuf* win_ws = nullptr) {
+  int rc = check_common(ctx, f, p, n_pairs);
+  if (rc) return rc;
+  if (!d_left || !d_right || !d_out) return fail(ctx, USV_ERR_INVALID_ARG, "null device pointer");
+  if (!aligned16(d_left) || !aligned16(d_right) || (f->row_stride & 15) || (f->frame_stride & 15))
+    return fail(ctx, USV_ERR_INVALID_ARG, "device frames need 16-byte aligned base, row_stride and frame_stride");
+  if (d_out->raw_cost_u16 && (rc = check_cost_u16(ctx, f, p))) return rc;
+  if (n_pairs == 0) return USV_OK;
+  CU(cudaSetDevice(ctx->device));
+  DevJob J;
+  fill_job(ctx, J, d_left, d_right, f, p, d_out);
+  const bool sparse = d_tx != nullptr;
+  if (sparse) {
+    if (!d_ty || n_templates < 0) return fail(ctx, USV_ERR_INVALID_ARG, "bad template list");
+    if (n_templates == 0) return USV_OK;
+    J.tx = d_tx; J.ty = d_ty; J.n_templates = n_templates;
+    J.cost_rows = d_cost_rows; J.score_rows = d_score_rows; J.row_cap = row_cap;
+    if ((d_cost_rows || d_score_rows) && row_cap <= 0) return fail(ctx, USV_ERR_INVALID_ARG, "row_cap must be positive");
+  }
+  if (J.out.distance || J.out.distance_f32) {
+    rc = ensure_lut(ctx, p->distance_kind, f->width, st, &J.dist_lut);
+    if (rc) return rc;
+  }
+  // resolved disparity map: ResolveMatchList over the winners on the device (usv_resolve_rows.cu). It reads the
+  // winners' RightIndex and value: the caller's arrays when they were asked for, scratch otherwise.
+  const bool want_resolved = d_out->resolved_disparity_u16 != nullptr;
+  if (want_resolved) {
+    if (sparse) return fail(ctx, USV_ERR_UNSUPPORTED, "resolved_disparity_u16 is an output of the dense sweep");
+    if (!usv::resolve_rows_supported(J.nx, J.nxc)) return fail(ctx, USV_ERR_UNSUPPORTED, "resolved_disparity_u16: rows wider than 2048 windows");
+    const bool integer = p->cost_kind <= USV_COST_SSD;
+    const size_t n_res = (size_t)J.n_templates * n_pairs;
+    if (!J.out.matches && (!integer || !J.out.right_index || !J.out.raw_cost)) {
+      DevBuf& ws = win_ws ? *win_ws : ctx->win_ws;
+      if (integer) {
+        if ((rc = grow(ctx, ws, n_res * 8))) return rc;
+        if (!J.out.right_index) J.out.right_index = (uint32_t*)ws.p;
+        if (!J.out.raw_cost) J.out.raw_cost = (uint32_t*)ws.p + n_res;
+      } else {
+        if ((rc = grow(ctx, ws, n_res * sizeof(usv_match)))) return rc;
+        J.out.matches = (usv_match*)ws.p;
+      }
+    }
+  }
+  if ((rc = dispatch_match(ctx, J, n_pairs, sparse, st, corr_ws))) return rc;
+  if (want_resolved) {
+    const bool from_matches = J.out.matches != nullptr && !(p->cost_kind <= USV_COST_SSD && J.out.right_index && J.out.raw_cost);
+    cudaError_t e = usv::launch_resolve_rows(from_matches ? nullptr : J.out.right_index, from_matches ? nullptr : J.out.raw_cost,
+                                             from_matches ? J.out.matches : nullptr, J.nx, J.ny, J.sx, J.nxc, J.n_templates, J.camera_side,
+                                             n_pairs, d_out->resolved_disparity_u16, st);
+    if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "resolve rows launch: %s", cudaGetErrorString(e));
+    ctx->launches++;
+  }
   return USV_OK;
 }
 
@@ -520,6 +570,88 @@ extern "C" int usv_resolve_match_list(usv_ctx* ctx, const usv_match* h_in, int64
   return USV_OK;
 }
 
+// ---- generate -> resolve -> distance in one call, host buffers (the reference's call order, P/Main.cpp:1115-1143) ----
+static int grow_pinned(usv_ctx* ctx, int k, size_t bytes) {
+  if (bytes <= ctx->pin_cap[k]) return USV_OK;
+  if (ctx->pin[k]) { CU(cudaFreeHost(ctx->pin[k])); ctx->pin[k] = nullptr; ctx->pin_cap[k] = 0; }
+  const size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaHostAlloc(&ctx->pin[k], want, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(ctx, USV_ERR_NOMEM, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+  ctx->pin_cap[k] = want;
+  return USV_OK;
+}
+
+extern "C" int usv_block_search_host(usv_ctx* ctx, const uint8_t* h_left, const uint8_t* h_right, const usv_frame_desc* f,
+                                     const usv_search_params* p, usv_match* h_matches, double* h_distance, int64_t cap, int64_t* n_out) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  int rc = check_common(ctx, f, p, 1);
+  if (rc) return rc;
+  if (!h_left || !h_right || !n_out || cap < 0 || (cap > 0 && !h_matches)) return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  *n_out = 0;
+  int32_t nx, ny;
+  if (usv_grid_dims(f, p, &nx, &ny, nullptr)) return fail(ctx, USV_ERR_INVALID_ARG, "bad geometry");
+  const int64_t n_win = (int64_t)nx * ny;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // frames: caller memory -> pinned staging at the device pitch (one host pass; the H2D is then one asynchronous copy
+  // per camera) -> HBM
+  const int row_bytes = f->width * f->channels, pitch = (row_bytes + 127) & ~127;
+  const size_t fbytes = (size_t)pitch * f->height;
+  if ((rc = grow_pinned(ctx, 0, 2 * fbytes))) return rc;
+  uint8_t* stage = (uint8_t*)ctx->pin[0];
+  for (int k = 0; k < 2; ++k) {
+    const uint8_t* src = k ? h_right : h_left;
+    uint8_t* dst = stage + k * fbytes;
+    if (f->row_stride == pitch) memcpy(dst, src, fbytes);
+    else for (int y = 0; y < f->height; ++y) memcpy(dst + (size_t)y * pitch, src + (size_t)y * f->row_stride, row_bytes);
+  }
+  if ((rc = grow(ctx, ctx->in_l, fbytes)) || (rc = grow(ctx, ctx->in_r, fbytes))) return rc;
+  CU(cudaMemcpyAsync(ctx->in_l.p, stage, fbytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->in_r.p, stage + fbytes, fbytes, cudaMemcpyHostToDevice, st));
+  usv_frame_desc df = *f;
+  df.row_stride = pitch; df.frame_stride = (int64_t)fbytes;
+  // generate (+ per-window first minimum): the winners stay in HBM
+  if ((rc = grow(ctx, ctx->out[0], sizeof(usv_match) * n_win))) return rc;
+  usv_outputs d_out;
+  memset(&d_out, 0, sizeof(d_out));
+  d_out.matches = (usv_match*)ctx->out[0].p;
+  if ((rc = match_device(ctx, (const uint8_t*)ctx->in_l.p, (const uint8_t*)ctx->in_r.p, &df, 1, p, &d_out, nullptr, nullptr, 0, nullptr,
+                         nullptr, 0, st)))
+    return rc;
+  const char* match_kernel = ctx->last_kernel;
+  // resolve: the reference's whole-list greedy pass over the accepted winners (usv_resolve.cu)
+  if ((rc = grow(ctx, ctx->misc[1], sizeof(usv_match) * n_win)) || (rc = grow(ctx, ctx->misc[2], sizeof(int64_t)))) return rc;
+  if ((rc = resolve_device(ctx, d_out.matches, n_win, 1, (usv_match*)ctx->misc[1].p, n_win, (int64_t*)ctx->misc[2].p, st))) return rc;
+  // distance of every surviving match (P/Main.cpp:681-694)
+  const bool want_dist = h_distance != nullptr && p->distance_kind != USV_DIST_NONE;
+  if (want_dist) {
+    const double* lut = nullptr;
+    if ((rc = ensure_lut(ctx, p->distance_kind, f->width, st, &lut))) return rc;
+    if ((rc = grow(ctx, ctx->misc[3], sizeof(double) * n_win))) return rc;
+    CU(usv::launch_match_list_distance((const usv_match*)ctx->misc[1].p, (const long long*)ctx->misc[2].p, n_win, nx, p->stride_x,
+                                       f->width - p->tmpl_w + 1, p->camera_side, p->distance_kind, lut, ctx->lut_n[p->distance_kind],
+                                       (double*)ctx->misc[3].p, st));
+    ctx->launches++;
+  }
+  ctx->last_kernel = match_kernel;
+  // results: count first, then exactly the surviving records through pinned staging
+  if ((rc = grow_pinned(ctx, 1, sizeof(usv_match) * n_win + 64)) || (rc = grow_pinned(ctx, 2, sizeof(double) * n_win + 64))) return rc;
+  int64_t* h_n = (int64_t*)((uint8_t*)ctx->pin[1] + sizeof(usv_match) * n_win);
+  CU(cudaMemcpyAsync(h_n, ctx->misc[2].p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int64_t total = *h_n, m = total < cap ? total : cap;
+  if (m > 0) {
+    CU(cudaMemcpyAsync(ctx->pin[1], ctx->misc[1].p, sizeof(usv_match) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    if (want_dist) CU(cudaMemcpyAsync(ctx->pin[2], ctx->misc[3].p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(h_matches, ctx->pin[1], sizeof(usv_match) * (size_t)m);
+    if (want_dist) memcpy(h_distance, ctx->pin[2], sizeof(double) * (size_t)m);
+    else if (h_distance) memset(h_distance, 0, sizeof(double) * (size_t)m);
+  }
+  *n_out = total;
+  return check_dev_status(ctx);
+}
+
 // ---- pre-pass (usv_preprocess.cu) -------------------------------------------------------------
 static int preprocess_check(usv_ctx* ctx, int32_t n_frames, const usv_preprocess_params* p, const void* map1, const void* map2) {
   if (!p) return fail(ctx, USV_ERR_INVALID_ARG, "null params");
@@ -604,6 +736,19 @@ extern "C" int usv_id_matcher(usv_ctx* ctx, const usv_match* h_cur, int64_t n_cu
   const int64_t m = total < cap ? total : cap;
   if (m > 0) CU(cudaMemcpy(h_out3, ctx->misc[2].p, sizeof(int32_t) * 3 * (size_t)m, cudaMemcpyDeviceToHost));
   *n_out = total;
+  return USV_OK;
+}
+
+extern "C" int usv_distance_lut(usv_ctx* ctx, int32_t kind, int32_t n, double* h_lut) {
+  if (!ctx) return USV_ERR_INVALID_ARG;
+  if (n <= 0 || !h_lut) return fail(ctx, USV_ERR_INVALID_ARG, "bad arguments");
+  if (kind != USV_DIST_PINHOLE && kind != USV_DIST_POWERLAW) return fail(ctx, USV_ERR_INVALID_ARG, "unknown distance_kind %d", kind);
+  CU(cudaSetDevice(ctx->device));
+  const double* lut = nullptr;
+  int rc = ensure_lut(ctx, kind, n, ctx->stream, &lut);  // the table the kernels' epilogue reads
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_lut, lut, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return USV_OK;
 }
 
@@ -780,6 +925,7 @@ struct Slot {
   uint8_t *h_l = nullptr, *h_r = nullptr, *d_l = nullptr, *d_r = nullptr;
   usv_outputs h_out, d_out;
   DevBuf corr_ws;  // planes + window statistics of the sliding correlation kernel: per slot, the slots run concurrently
+  DevBuf win_ws;   // winners (RightIndex + value) for the resolved disparity map when the caller did not ask for them
 };
 
 struct usv_stream {
@@ -803,6 +949,7 @@ extern "C" int usv_stream_destroy(usv_stream* s) {
     if (sl.d_l) cudaFree(sl.d_l);
     if (sl.d_r) cudaFree(sl.d_r);
     if (sl.corr_ws.p) cudaFree(sl.corr_ws.p);
+    if (sl.win_ws.p) cudaFree(sl.win_ws.p);
     for (int i = 0; i < kNumOut; ++i) {
       if (*out_slot(&sl.h_out, i)) cudaFreeHost(*out_slot(&sl.h_out, i));
       if (*out_slot(&sl.d_out, i)) cudaFree(*out_slot(&sl.d_out, i));
@@ -881,16 +1028,18 @@ extern "C" int usv_stream_frame_desc(const usv_stream* s, usv_frame_desc* out) {
 }
 
 // kernels + D2H + completion event of a slot whose frames are already enqueued on its stream
-static int enqueue_match_and_results(usv_stream* s, Slot& sl, int32_t n_pairs) {
+// (h_dst: the caller's own result arrays instead of the slot's pinned ones — usv_stream_submit_io)
+static int enqueue_match_and_results(usv_stream* s, Slot& sl, int32_t n_pairs, usv_outputs* h_dst = nullptr) {
   usv_ctx* ctx = s->ctx;
   if (n_pairs > 0) {
     int rc = match_device(ctx, sl.d_l, sl.d_r, &s->df, n_pairs, &s->params, &sl.d_out, nullptr, nullptr, 0, nullptr, nullptr, 0, sl.st,
-                          &sl.corr_ws);
+                          &sl.corr_ws, &sl.win_ws);
     if (rc) return rc;
     const size_t n_res = (size_t)s->n_win * n_pairs;
     for (int i = 0; i < kNumOut; ++i)
       if (*out_slot(&sl.h_out, i))
-        CU(cudaMemcpyAsync(*out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res, cudaMemcpyDeviceToHost, sl.st));
+        CU(cudaMemcpyAsync(h_dst ? *out_slot(h_dst, i) : *out_slot(&sl.h_out, i), *out_slot(&sl.d_out, i), kOutElem[i] * n_res,
+                           cudaMemcpyDeviceToHost, sl.st));
   }
   CU(cudaEventRecord(sl.done, sl.st));
   return USV_OK;
@@ -981,6 +1130,26 @@ extern "C" int usv_stream_submit_gather(usv_stream* s, int32_t slot, const uint8
     }
   }
   return enqueue_match_and_results(s, sl, n_pairs);
+}
+
+extern "C" int usv_stream_submit_io(usv_stream* s, int32_t slot, const uint8_t* h_left, const uint8_t* h_right, const usv_frame_desc* hf,
+                                    int32_t n_pairs, const usv_outputs* h_dst) {
+  if (!s || slot < 0 || slot >= s->n_slots) return USV_ERR_INVALID_ARG;
+  usv_ctx* ctx = s->ctx;
+  if (!h_left || !h_right || !hf || !h_dst) return fail(ctx, USV_ERR_INVALID_ARG, "null pointer");
+  if (n_pairs < 0 || n_pairs > s->pairs_per_slot) return fail(ctx, USV_ERR_INVALID_ARG, "n_pairs %d exceeds the slot", n_pairs);
+  int rc = check_host_frame(s, hf);
+  if (rc) return rc;
+  usv_outputs dst = *h_dst;
+  for (int i = 0; i < kNumOut; ++i)
+    if (((s->mask >> i) & 1u) && !*out_slot(&dst, i)) return fail(ctx, USV_ERR_INVALID_ARG, "destination of output %d of the stream's mask is null", i);
+  CU(cudaSetDevice(ctx->device));
+  Slot& sl = s->slots[slot];
+  if (n_pairs > 0) {
+    if ((rc = enqueue_frames(s, sl, sl.d_l, h_left, hf, n_pairs))) return rc;
+    if ((rc = enqueue_frames(s, sl, sl.d_r, h_right, hf, n_pairs))) return rc;
+  }
+  return enqueue_match_and_results(s, sl, n_pairs, &dst);
 }
 
 extern "C" int usv_host_register(usv_ctx* ctx, void* p, size_t bytes) {

@@ -1,6 +1,8 @@
 // usv_distance.cu — the DistanceCalculator family as sm_100a kernels.
 // Each kernel follows the reference's arithmetic operation by operation
 // (explicit _rn intrinsics: no FMA contraction), one thread per object.
+#include <algorithm>
+
 #include "usv_common.cuh"
 
 namespace usv {
@@ -89,6 +91,29 @@ __global__ void coordinate_position_kernel(int camera_side, const double* __rest
   if (camera_side) Z = __ddiv_rn(__dsub_rn(Z, 0.6112), 2.228);                                         // :131
   else Z = __ddiv_rn(__dsub_rn(Z, 6.3706), 2.5771);                                                    // :134
   xyz[3 * i] = X; xyz[3 * i + 1] = Y; xyz[3 * i + 2] = Z;
+}
+
+// Distance of every record of a resolved match list over a dense window grid (the inline disparity + distance of
+// P/Main.cpp:681-694 applied to TentativeMatch): window x = (LeftIndex mod nx) * sx, candidate x' = RightIndex mod nxc,
+// disp = x - x' (LeftCam) / x' - x (RightCam). n lives in device memory (the resolve kernel wrote it).
+__global__ void match_list_distance_kernel(const usv_match* __restrict__ list, const long long* __restrict__ n_dev, long long cap, int nx,
+                                           int sx, int nxc, int camera_side, int kind, const double* __restrict__ lut, int lut_n,
+                                           double* __restrict__ out) {
+  const long long n = min(*n_dev, cap);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const usv_match m = list[i];
+    const int x = (int)(m.LeftIndex % (uint32_t)nx) * sx, xr = (int)(m.RightIndex % (uint32_t)nxc);
+    const int d = camera_side == USV_LEFT_CAM ? x - xr : xr - x;
+    out[i] = (lut && d >= 0 && d < lut_n) ? lut[d] : distance_from_disparity(d, kind);
+  }
+}
+
+cudaError_t launch_match_list_distance(const usv_match* d_list, const long long* d_n, long long cap, int nx, int sx, int nxc, int camera_side,
+                                       int kind, const double* lut, int lut_n, double* d_out, cudaStream_t st) {
+  if (cap <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)std::min<long long>((cap + 255) / 256, 148 * 8);
+  match_list_distance_kernel<<<blocks, 256, 0, st>>>(d_list, d_n, cap, nx, sx, nxc, camera_side, kind, lut, lut_n, d_out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_disparity_to_distance(const int* d_disp, long long n, int kind, double* d_out, cudaStream_t st) {
