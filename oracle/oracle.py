@@ -37,12 +37,25 @@ def _stale(target, deps):
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def _same_cpu():
+    """The oracle is compiled with -march=native; a copy built on a host with other ISA extensions must not be loaded."""
+    sig = os.path.join(HERE, "_build", "cpu_flags.md5")
+    try:
+        import hashlib
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+        return open(sig).read().split()[0] == hashlib.md5(flags.encode()).hexdigest()
+    except Exception:
+        return True
+
+
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(HERE, f) for f in ("block_search_oracle.c", "distance_oracle.c", "contour_oracle.c", "Makefile")]
+        srcs = [os.path.join(HERE, f) for f in ("block_search_oracle.c", "distance_oracle.c", "contour_oracle.c", "sliding_sad_cpu.c", "Makefile")]
         srcs.append(os.path.join(HERE, "..", "include", "usv_b200.h"))
-        if _stale(ORACLE_SO, srcs):
+        if _stale(ORACLE_SO, srcs) or not _same_cpu():
+            if os.path.exists(ORACLE_SO):
+                os.remove(ORACLE_SO)  # built with -march=native for another CPU (the .so travels to the GPU box): rebuild here
             build()
         L = C.CDLL(ORACLE_SO)
         L.usv_oracle_distance.restype = C.c_double
@@ -56,6 +69,7 @@ def lib():
         L.usv_oracle_id_matcher.restype = C.c_int64
         L.usv_oracle_match_contours.restype = C.c_int64
         L.usv_oracle_match_shapes_i1.restype = C.c_double
+        L.usv_oracle_match_dense_sliding.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -142,6 +156,23 @@ def match_dense_rows(left, right, params, iy0, iy1, threads=0):
     if rc:
         raise RuntimeError("oracle match_dense_rows failed")
     return ri, rc_, ev.value
+
+
+def match_dense_sliding(left, right, params, iy0=0, iy1=None, threads=0):
+    """The sliding-window CPU arm (sliding_sad_cpu.c): raw winners of window rows [iy0, iy1) of every pair.
+    Returns (right_index [n, ny*nx], raw_cost [n, ny*nx], candidate evaluations done); rows outside stay NO_MATCH / ~0."""
+    left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+    f = _abi.frame_desc_for(left)
+    nx, ny, _ = grid_dims(f, params)
+    n = left.shape[0]
+    iy1 = ny if iy1 is None else iy1
+    ri = np.full(n * nx * ny, 0xFFFFFFFF, np.uint32)
+    rc = np.full(n * nx * ny, 0xFFFFFFFF, np.uint32)
+    ev = lib().usv_oracle_match_dense_sliding(_ptr(left), _ptr(right), C.byref(f), C.c_int32(n), C.byref(params), C.c_int32(iy0), C.c_int32(iy1),
+                                              _ptr(ri), _ptr(rc), C.c_int32(threads))
+    if ev < 0:
+        raise RuntimeError("sliding CPU arm: unsupported job")
+    return ri.reshape(n, ny * nx), rc.reshape(n, ny * nx), int(ev)
 
 
 def match_templates(left, right, tx, ty, params, mask=ALL_OUTPUTS, rows=False):

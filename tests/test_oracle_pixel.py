@@ -152,3 +152,29 @@ def test_empty_candidate_range(oracle):
     assert (out["right_index"][0].reshape(9, nx)[:, :10] == _abi.NO_MATCH).all()  # x - 10 < 0: no candidates
     assert (out["raw_cost"][0].reshape(9, nx)[:, :10] == 0xFFFFFFFF).all()
     assert np.isinf(out["matches"]["MatchValue"][0].reshape(9, nx)[:, :10]).all()
+
+
+@pytest.mark.parametrize("w,h,tw,th,kw", [
+    (160, 40, 16, 16, dict()),                                                     # fast path, full range
+    (200, 36, 16, 16, dict(search_min=3, search_max=70)),
+    (131, 30, 16, 12, dict(camera_side=_abi.RIGHT_CAM, search_max=40)),
+    (120, 28, 16, 16, dict(search_min=-9, search_max=9)),                          # signed range
+    (97, 25, 7, 5, dict(search_max=33)),                                           # generic path
+    (90, 40, 32, 32, dict(camera_side=_abi.RIGHT_CAM)),
+])
+def test_sliding_cpu_arm_equals_direct_form(oracle, w, h, tw, th, kw):
+    """bench.py's algorithm-matched CPU arm (oracle/sliding_sad_cpu.c: column sums slid down the rows, window sums along x — the
+    GPU kernel's formulation) returns exactly the direct-form oracle's winners and costs, ties included."""
+    left, right = synth.make_pairs(2, w, h, 1, shift=7, noise_sigma=2.0, seed=w)
+    left[1, : h // 2] = 50; right[1, : h // 2] = 50  # flat half: every candidate ties
+    p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost="sad", accept_threshold=10.0, **kw)
+    exp = oracle.match_dense(left, right, p)
+    ri, rc, ev = oracle.match_dense_sliding(left, right, p, threads=3)
+    assert np.array_equal(ri, exp["right_index"]) and np.array_equal(rc, exp["raw_cost"])
+    f = _abi.frame_desc_for(left)
+    assert ev == 2 * oracle.grid_dims(f, p)[2]
+    # a row range only (what the bench samples)
+    nx, ny, _ = oracle.grid_dims(f, p)
+    ri2, rc2, _ = oracle.match_dense_sliding(left, right, p, 2, min(ny, 9))
+    assert np.array_equal(ri2.reshape(2, ny, nx)[:, 2:9], exp["right_index"].reshape(2, ny, nx)[:, 2:9])
+    assert np.array_equal(rc2.reshape(2, ny, nx)[:, 2:9], exp["raw_cost"].reshape(2, ny, nx)[:, 2:9])

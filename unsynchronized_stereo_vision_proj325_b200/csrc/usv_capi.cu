@@ -28,8 +28,15 @@ cudaError_t launch_resolve(const usv_match* d_in, long long n, int skip_unmatche
                            void* d_ws, size_t ws_bytes, cudaStream_t st, int* n_launches);
 size_t id_matcher_workspace_bytes(long long n_cur);
 bool resolve_rows_supported(int nx, int nxc);
-cudaError_t launch_resolve_rows(const uint32_t* d_right_index, const uint32_t* d_raw_cost, const usv_match* d_matches, int nx, int ny, int sx,
-                                int nxc, long long n_templates, int camera_side, int n_pairs, uint16_t* d_out, cudaStream_t st);
+struct ResolveRowsSrc {
+  const uint16_t* disparity_u16;
+  const uint16_t* raw_cost_u16;
+  const uint32_t* raw_cost;
+  const uint32_t* right_index;
+  const usv_match* matches;
+};
+cudaError_t launch_resolve_rows(const ResolveRowsSrc& S, bool integer_values, int nx, int ny, int sx, int nxc, long long n_templates,
+                                int camera_side, int n_pairs, uint16_t* d_out, cudaStream_t st);
 cudaError_t launch_id_matcher(const usv_match* d_cur, long long n_cur, const usv_match* d_old, long long n_old, int* d_out3,
                               long long cap, long long* d_n_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
 size_t preprocess_scratch_bytes(int width, int height, int n_frames);
@@ -372,12 +379,14 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
     if (!usv::resolve_rows_supported(J.nx, J.nxc)) return fail(ctx, USV_ERR_UNSUPPORTED, "resolved_disparity_u16: rows wider than 2048 windows");
     const bool integer = p->cost_kind <= USV_COST_SSD;
     const size_t n_res = (size_t)J.n_templates * n_pairs;
-    if (!J.out.matches && (!integer || !J.out.right_index || !J.out.raw_cost)) {
+    const bool have_int = integer && ((J.out.disparity_u16 && (J.out.raw_cost_u16 || J.out.raw_cost)) || (J.out.right_index && J.out.raw_cost));
+    if (!have_int && !(J.out.matches && !integer)) {
       DevBuf& ws = win_ws ? *win_ws : ctx->win_ws;
-      if (integer) {
-        if ((rc = grow(ctx, ws, n_res * 8))) return rc;
-        if (!J.out.right_index) J.out.right_index = (uint32_t*)ws.p;
-        if (!J.out.raw_cost) J.out.raw_cost = (uint32_t*)ws.p + n_res;
+      if (integer) {  // disparity (2 B) + cost (4 B, or what the caller already asked for)
+        const bool need_cost = !J.out.raw_cost && !J.out.raw_cost_u16;
+        if ((rc = grow(ctx, ws, n_res * (need_cost ? 6 : 2) + 16))) return rc;
+        if (need_cost) J.out.raw_cost = (uint32_t*)ws.p;
+        if (!J.out.disparity_u16) J.out.disparity_u16 = (uint16_t*)((uint32_t*)ws.p + (need_cost ? n_res : 0));
       } else {
         if ((rc = grow(ctx, ws, n_res * sizeof(usv_match)))) return rc;
         J.out.matches = (usv_match*)ws.p;
@@ -386,10 +395,18 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
   }
   if ((rc = dispatch_match(ctx, J, n_pairs, sparse, st, corr_ws))) return rc;
   if (want_resolved) {
-    const bool from_matches = J.out.matches != nullptr && !(p->cost_kind <= USV_COST_SSD && J.out.right_index && J.out.raw_cost);
-    cudaError_t e = usv::launch_resolve_rows(from_matches ? nullptr : J.out.right_index, from_matches ? nullptr : J.out.raw_cost,
-                                             from_matches ? J.out.matches : nullptr, J.nx, J.ny, J.sx, J.nxc, J.n_templates, J.camera_side,
-                                             n_pairs, d_out->resolved_disparity_u16, st);
+    const bool integer = p->cost_kind <= USV_COST_SSD;
+    usv::ResolveRowsSrc S;
+    memset(&S, 0, sizeof(S));
+    if (integer && J.out.disparity_u16 && (J.out.raw_cost_u16 || J.out.raw_cost)) {
+      S.disparity_u16 = J.out.disparity_u16; S.raw_cost_u16 = J.out.raw_cost_u16; S.raw_cost = J.out.raw_cost;
+    } else if (integer && J.out.right_index && J.out.raw_cost) {
+      S.right_index = J.out.right_index; S.raw_cost = J.out.raw_cost;
+    } else {
+      S.matches = J.out.matches;
+    }
+    cudaError_t e = usv::launch_resolve_rows(S, S.matches == nullptr, J.nx, J.ny, J.sx, J.nxc, J.n_templates, J.camera_side, n_pairs,
+                                             d_out->resolved_disparity_u16, st);
     if (e != cudaSuccess) return fail(ctx, USV_ERR_CUDA, "resolve rows launch: %s", cudaGetErrorString(e));
     ctx->launches++;
   }

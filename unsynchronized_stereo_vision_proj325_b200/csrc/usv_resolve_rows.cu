@@ -13,33 +13,20 @@
 // windows that claim the same x' the later one survives unless it is strictly worse... and the earlier one survives
 // too when it is not strictly worse than every later claimant — the reference's quirk, kept.
 //
-// One CTA per (window row, pair): block radix sort of the row's records by (x', descending x), segmented exclusive
-// prefix-min of the values (= min over the LATER windows of the same x'), one compare, scatter of the disparity or
-// USV_NO_DISPARITY. Values are compared as the integers they are (SAD / SSD raw costs: MatchValue = raw / const is
-// strictly monotone) or as order-preserving bit patterns of the f64 MatchValue (NCC / ZNCC). Unmatched windows
-// (RightIndex == USV_NO_MATCH: no candidate passed the accept test, :417) take no part, as in the C++ wrapper.
-#include <cub/block/block_radix_sort.cuh>
-#include <cub/block/block_scan.cuh>
-
+// One CTA per (window row, pair), everything in shared memory: the row's (x', value) pairs, and last[x'] = the last window
+// that claims x' and min[x'] = the smallest value among its claimants (two shared-memory atomics per window). A window that
+// holds its bucket's minimum, or is its last claimant, survives without further work; any other window scans the later
+// windows up to last[x'] for a strictly smaller value of the same x'. In textured frames almost every bucket has one
+// member, in flat frames whole rows tie at the minimum: the scan only runs for genuinely contested candidates.
+// Values are compared as the integers they are (SAD / SSD raw costs: MatchValue = raw / const is strictly monotone) or
+// as order-preserving bit patterns of the f64 MatchValue (NCC / ZNCC). Unmatched windows (RightIndex == USV_NO_MATCH:
+// no candidate passed the accept test, :417) take no part, as in the C++ wrapper.
 #include "usv_common.cuh"
 
 namespace usv {
 
-constexpr int kRRThreads = 128;
-constexpr int kRRBits = 11;  // x and x' below 2048
-
-struct SegMin {
-  uint32_t bucket;
-  unsigned long long v;
-};
-struct SegMinOp {
-  __device__ __forceinline__ SegMin operator()(const SegMin& a, const SegMin& b) const {
-    SegMin r;
-    r.bucket = b.bucket;
-    r.v = (a.bucket == b.bucket && a.v < b.v) ? a.v : b.v;
-    return r;
-  }
-};
+constexpr int kRRThreads = 256;
+constexpr int kRRMax = 2048;  // windows per row and candidate positions per row
 
 // order-preserving map of an f64 onto u64 (NaN never occurs in a winner record)
 __device__ __forceinline__ unsigned long long f64_ordered(double d) {
@@ -47,82 +34,80 @@ __device__ __forceinline__ unsigned long long f64_ordered(double d) {
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-template <int ITEMS>
-__global__ void __launch_bounds__(kRRThreads) dense_resolve_rows_kernel(const uint32_t* __restrict__ right_index, const uint32_t* __restrict__ raw_cost,
-                                                                         const usv_match* __restrict__ matches, int nx, int sx, int nxc,
-                                                                         long long n_templates, int camera_side, uint16_t* __restrict__ out) {
-  typedef cub::BlockRadixSort<uint32_t, kRRThreads, ITEMS, unsigned long long> Sort;
-  typedef cub::BlockScan<SegMin, kRRThreads> Scan;
-  __shared__ union {
-    typename Sort::TempStorage sort;
-    typename Scan::TempStorage scan;
-  } tmp;
+// Where the winners of the sweep live (the first complete source is used):
+//   disparity_u16 + raw_cost_u16 / raw_cost   (integer kinds; x' = x -/+ d)
+//   right_index   + raw_cost                  (integer kinds)
+//   matches                                   (any kind; values compared as f64)
+struct ResolveRowsSrc {
+  const uint16_t* disparity_u16;
+  const uint16_t* raw_cost_u16;
+  const uint32_t* raw_cost;
+  const uint32_t* right_index;
+  const usv_match* matches;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(kRRThreads) dense_resolve_rows_kernel(const ResolveRowsSrc S, int nx, int sx, int nxc, long long n_templates,
+                                                                         int camera_side, uint16_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  V* s_v = reinterpret_cast<V*>(rr_smem);                     // [nx] value of the window's winner
+  V* s_min = s_v + nx;                                        // [nxc] smallest value among the claimants of x'
+  int* s_last = reinterpret_cast<int*>(s_min + nxc);          // [nxc] last window that claims x'
+  uint16_t* s_xr = reinterpret_cast<uint16_t*>(s_last + nxc); // [nx] x' of the winner, 0xFFFF = unmatched
   const int iy = blockIdx.x, pair = blockIdx.y, tid = threadIdx.x;
   const long long g0 = (long long)pair * n_templates + (long long)iy * nx;
-  uint32_t key[ITEMS];
-  unsigned long long val[ITEMS];
-#pragma unroll
-  for (int k = 0; k < ITEMS; ++k) {
-    const int i = tid * ITEMS + k;
-    key[k] = 0xffffffffu;
-    val[k] = ~0ull;
-    if (i < nx) {
-      const uint32_t ri = matches ? matches[g0 + i].RightIndex : right_index[g0 + i];
-      if (ri != USV_NO_MATCH) {
-        const uint32_t xr = ri % (uint32_t)nxc;
-        key[k] = (xr << kRRBits) | (uint32_t)((1 << kRRBits) - 1 - i);
-        val[k] = matches ? f64_ordered(matches[g0 + i].MatchValue) : (unsigned long long)raw_cost[g0 + i];
-      }
-    }
-  }
-  Sort(tmp.sort).Sort(key, val, 0, 2 * kRRBits + 1);  // bit 22 separates the unmatched windows (key ~0) from x' = 2047
-  __syncthreads();
-  // inclusive segmented min over the thread's items, block-wide exclusive scan of the thread aggregates
-  SegMin run[ITEMS];
-  SegMinOp op;
-#pragma unroll
-  for (int k = 0; k < ITEMS; ++k) {
-    SegMin s;
-    s.bucket = key[k] >> kRRBits;
-    s.v = val[k];
-    run[k] = k == 0 ? s : op(run[k - 1], s);
-  }
-  SegMin before;
-  SegMin id;
-  id.bucket = 0xfffffffeu;  // no bucket: the first thread has nothing before it
-  id.v = ~0ull;
-  Scan(tmp.scan).ExclusiveScan(run[ITEMS - 1], before, id, op);
-#pragma unroll
-  for (int k = 0; k < ITEMS; ++k) {
-    if (key[k] == 0xffffffffu) continue;  // unmatched (or beyond the row); their map entries are written below
-    const SegMin prev = k == 0 ? before : op(before, run[k - 1]);
-    const uint32_t bucket = key[k] >> kRRBits;
-    const bool beaten = prev.bucket == bucket && prev.v < val[k];  // a later window claims the same x' with a strictly smaller value
-    const int i = (1 << kRRBits) - 1 - (int)(key[k] & ((1u << kRRBits) - 1));
-    const int x = i * sx, xr = (int)bucket;
-    const int d = camera_side == USV_LEFT_CAM ? x - xr : xr - x;
-    out[g0 + i] = beaten ? (uint16_t)USV_NO_DISPARITY : (uint16_t)d;
-  }
-  // unmatched windows
+  const bool left = camera_side == USV_LEFT_CAM;
+  for (int k = tid; k < nxc; k += kRRThreads) { s_last[k] = -1; s_min[k] = ~(V)0; }
   for (int i = tid; i < nx; i += kRRThreads) {
-    const uint32_t ri = matches ? matches[g0 + i].RightIndex : right_index[g0 + i];
-    if (ri == USV_NO_MATCH) out[g0 + i] = (uint16_t)USV_NO_DISPARITY;
+    uint32_t xr = 0xFFFFu;
+    V v = 0;
+    if (sizeof(V) == 4 && S.disparity_u16) {
+      const uint32_t d = S.disparity_u16[g0 + i];
+      if (d != USV_NO_DISPARITY) {
+        xr = (uint32_t)(left ? i * sx - (int)d : i * sx + (int)d);
+        v = (V)(S.raw_cost_u16 ? (uint32_t)S.raw_cost_u16[g0 + i] : S.raw_cost[g0 + i]);
+      }
+    } else if (sizeof(V) == 4 && S.right_index) {
+      const uint32_t ri = S.right_index[g0 + i];
+      if (ri != USV_NO_MATCH) { xr = ri % (uint32_t)nxc; v = (V)S.raw_cost[g0 + i]; }
+    } else {
+      const usv_match m = S.matches[g0 + i];
+      if (m.RightIndex != USV_NO_MATCH) { xr = m.RightIndex % (uint32_t)nxc; v = (V)f64_ordered(m.MatchValue); }
+    }
+    s_xr[i] = (uint16_t)xr;
+    s_v[i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < nx; i += kRRThreads) {
+    const uint32_t xr = s_xr[i];
+    if (xr != 0xFFFFu) { atomicMax(&s_last[xr], i); atomicMin(&s_min[xr], s_v[i]); }
+  }
+  __syncthreads();
+  for (int i = tid; i < nx; i += kRRThreads) {
+    const uint32_t xr = s_xr[i];
+    uint16_t r = (uint16_t)USV_NO_DISPARITY;
+    if (xr != 0xFFFFu) {
+      const V v = s_v[i];
+      const int last = s_last[xr];
+      bool beaten = false;
+      // nobody is strictly better than the bucket's minimum: no scan (flat frames, where whole rows tie, stay cheap)
+      if (v > s_min[xr])
+        for (int j = i + 1; j <= last && !beaten; ++j) beaten = s_xr[j] == xr && s_v[j] < v;  // a later claimant, strictly better (:450-451)
+      if (!beaten) r = (uint16_t)(left ? i * sx - (int)xr : (int)xr - i * sx);
+    }
+    out[g0 + i] = r;
   }
 }
 
-bool resolve_rows_supported(int nx, int nxc) { return nx <= kRRThreads * 16 && nxc <= (1 << kRRBits) && nx <= (1 << kRRBits); }
+bool resolve_rows_supported(int nx, int nxc) { return nx <= kRRMax && nxc <= kRRMax; }
 
-// Winners come from `matches` (any cost kind) or from right_index + raw_cost (integer kinds); one launch for the batch.
-cudaError_t launch_resolve_rows(const uint32_t* d_right_index, const uint32_t* d_raw_cost, const usv_match* d_matches, int nx, int ny, int sx,
-                                int nxc, long long n_templates, int camera_side, int n_pairs, uint16_t* d_out, cudaStream_t st) {
+cudaError_t launch_resolve_rows(const ResolveRowsSrc& S, bool integer_values, int nx, int ny, int sx, int nxc, long long n_templates,
+                                int camera_side, int n_pairs, uint16_t* d_out, cudaStream_t st) {
   if (!resolve_rows_supported(nx, nxc)) return cudaErrorNotSupported;
   const dim3 grid(ny, n_pairs), block(kRRThreads);
-#define USV_RR(IT) dense_resolve_rows_kernel<IT><<<grid, block, 0, st>>>(d_right_index, d_raw_cost, d_matches, nx, sx, nxc, n_templates, camera_side, d_out)
-  if (nx <= kRRThreads * 2) USV_RR(2);
-  else if (nx <= kRRThreads * 5) USV_RR(5);
-  else if (nx <= kRRThreads * 8) USV_RR(8);
-  else USV_RR(16);
-#undef USV_RR
+  const size_t smem = (size_t)(nx + nxc) * (integer_values ? 4 : 8) + (size_t)nxc * 4 + (size_t)nx * 2 + 16;
+  if (integer_values) dense_resolve_rows_kernel<uint32_t><<<grid, block, smem, st>>>(S, nx, sx, nxc, n_templates, camera_side, d_out);
+  else dense_resolve_rows_kernel<unsigned long long><<<grid, block, smem, st>>>(S, nx, sx, nxc, n_templates, camera_side, d_out);
   return cudaGetLastError();
 }
 
