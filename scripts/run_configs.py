@@ -76,4 +76,4 @@ dense("C2 geometry, ncc gray 16x16 full range", 64, 640, 480, 1, 3, tmpl_w=16, t
 dense("C2 geometry, zncc gray 16x16 full range", 64, 640, 480, 1, 3, tmpl_w=16, tmpl_h=16, cost="zncc")
 dense("C3geom 1280x720 colour 32x32 NCC D=256", 16, 1280, 720, 3, 1, tmpl_w=32, tmpl_h=32, cost="ncc", search_max=255)
 dense("C3geom 1280x720 colour 32x32 SSD D=256", 16, 1280, 720, 3, 1, tmpl_w=32, tmpl_h=32, cost="ssd", search_max=255)
-dense("C3geom 1280x720 colour 32x32 SAD-colour D=256", 8, 1280, 720, 3, 1, tmpl_w=32, tmpl_h=32, cost="sad", search_max=255)
+dense("C3geom 1280x720 colour 32x32 SAD-colour D=256", 32, 1280, 720, 3, 3, tmpl_w=32, tmpl_h=32, cost="sad", search_max=255)

@@ -17,7 +17,9 @@
 namespace usv {
 cudaError_t launch_direct(const DevJob& J, int n_pairs, cudaStream_t st);
 // returns cudaErrorNotSupported when the dense kernels do not cover the job
-cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches);
+size_t dense_scratch_bytes_per_pair(const DevJob& J);
+cudaError_t launch_dense(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
+                         int* n_launches);
 size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out);
 cudaError_t launch_dense_corr(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
                               int* n_launches);
@@ -311,7 +313,18 @@ static int dispatch_match(usv_ctx* ctx, const DevJob& J, int32_t n_pairs, bool s
   if (!sparse) {
     const char* name = nullptr;
     int nl = 0;
-    cudaError_t e = usv::launch_dense(J, n_pairs, st, &name, &nl);
+    // the scratch (colour planes here, planes + window statistics below) belongs to whoever owns the stream: launches on
+    // different streams must not share it
+    DevBuf& dws = corr_ws ? *corr_ws : ctx->corr_ws;
+    if (const size_t per_pair = (J.cost_kind == USV_COST_SAD && J.corr_kernel != USV_CORR_KERNEL_ALU) ? usv::dense_scratch_bytes_per_pair(J) : 0) {
+      const size_t cap = (size_t)3 << 29;  // 1.5 GB
+      size_t want = per_pair * (size_t)n_pairs;
+      if (want > cap) want = std::max(per_pair, cap / per_pair * per_pair);
+      if ((rc = grow(ctx, dws, want))) return rc;
+    }
+    cudaError_t e = (J.cost_kind == USV_COST_SAD && J.channels == 3 && J.corr_kernel == USV_CORR_KERNEL_ALU)
+                        ? cudaErrorNotSupported  // test / measurement aid: colour SAD on the ALU correlation kernel
+                        : usv::launch_dense(J, n_pairs, dws.p, dws.cap, st, &name, &nl);
     if (e == cudaSuccess) {
       ctx->launches += nl;
       ctx->last_kernel = name;

@@ -39,11 +39,9 @@
 namespace usv {
 
 constexpr int kDenseThreads = 128;
-constexpr int kRB = 4;          // rows per staging block
 constexpr int kLW = 32;         // words per L copy row (128 B)
 constexpr int kRW = 44;         // words per R copy row (40 used; 44 keeps the four copies on disjoint banks)
 constexpr int kRowWords = 4 * kLW + 4 * kRW;  // one ring row: 4 L copies + 4 R copies
-constexpr int kRingWords = 4 * kRB * kRowWords;  // entering + leaving halves, each double-buffered by block
 constexpr int kCodeOff = 32;    // candidate code = x0 -/+ d + kCodeOff: a valid candidate of column i has x0 -/+ d >= -4i >= -28
 
 struct DenseCfg {
@@ -56,6 +54,13 @@ struct DenseCfg {
   int x_off;        // tile t starts at x = t * stride_px - x_off (multiple of 4)
   int n_pairs;      // the grid is one-dimensional: chunks of pairs, inside a chunk tile-major, heaviest tiles first
   int chunk_pairs;
+  // where the rows come from: the frames themselves (one plane) or the planes buffer [pair][plane][H][pitch] the
+  // interleaved colour frames were split into (usv_dense_corr.cu: corr_planes_kernel)
+  const uint8_t* lp;
+  const uint8_t* rp;
+  long long pair_stride, plane_stride;
+  int pitch;        // bytes between rows of a plane
+  int pair0;        // first pair of this launch inside the caller's batch (outputs are indexed by the global pair)
 };
 
 __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c) {
@@ -75,7 +80,7 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // i0-1, i0-1-NW, ... and i1+NW-1, i1+2NW-1, ... start at BIG = 2^(31-xb) instead of 0. Every invalid
 // window then contains exactly one BIG column and its key carries bit 31 (true keys stay below 2^31,
 // checked on the host), every valid window contains none. No per-element masks, no second code path.
-template <int DIR, int NW, bool FOLD, bool RING2, int NJ = 4>
+template <int DIR, int NW, bool FOLD, bool RING2, int NPL, int NJ = 4>
 __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
                                            const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
                                            const int XR0, const int run, const int dbase, const int r_shift,
@@ -86,8 +91,11 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const int ul = run, dl = lane >> 2, q = dl & 3, jh = dl >> 2;
   const int x0 = X0 + p + 32 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i, i < 8)
   const bool guest = FOLD && (lane & 3) == 0;
+  constexpr int kRB = NPL == 1 ? 4 : 2;  // rows per staging block (a ring slot holds NPL plane rows)
+  constexpr int kSlotWords = NPL * kRowWords;
   const int th = J.th;
-  const int row_words = J.row_stride >> 2;
+  const int row_words = cfg.pitch >> 2;
+  const long long plane_words = cfg.plane_stride >> 2;
   const uint32_t key_scale = 1u << cfg.xb;
   const uint32_t minus_scale = key_scale * minus_one;  // -(1 << xb), kept opaque so the multiply stays an IMAD
   const uint32_t big = 1u << (31 - cfg.xb);
@@ -129,38 +137,43 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   // byte-shifted copies of its chunk: 12 funnel shifts, one STS.128 per copy.
   constexpr int kChunks = kLW / 4 + 10;
   struct StageTask {
-    const uint32_t* g;  // frame rows of the band (L or R)
+    const uint32_t* g;  // frame rows of the band (L or R), this task's plane
     int row, back;      // row inside the block; th for the leaving half, 0 for the entering half
     int gb;             // first global word of the chunk (before clamping to the frame row)
-    int off, kw;        // word offset inside the ring (half + copy 0 + chunk), words between copies
+    int off, kw;        // word offset inside the ring (half + plane + copy 0 + chunk), words between copies
     bool on;
   };
   auto make_task = [&](int k) {
     StageTask t;
-    t.on = k < (RING2 ? 2 : 1) * kRB * kChunks;
-    const int half = k >= kRB * kChunks ? 1 : 0, rem = k - half * kRB * kChunks;
-    t.row = rem / kChunks;
-    const int c = rem - t.row * kChunks;
+    constexpr int kHalfTasks = kRB * NPL * kChunks;
+    t.on = k < (RING2 ? 2 : 1) * kHalfTasks;
+    const int half = k >= kHalfTasks ? 1 : 0;
+    int rem = k - half * kHalfTasks;
+    t.row = rem / (NPL * kChunks);
+    rem -= t.row * (NPL * kChunks);
+    const int pl = rem / kChunks, c = rem - pl * kChunks;
     const bool left = c < kLW / 4;
     const int w = left ? 4 * c : 4 * (c - kLW / 4);
-    t.g = left ? Lg : Rg;
+    t.g = (left ? Lg : Rg) + (long long)pl * plane_words;
     t.back = half ? th : 0;
     t.gb = ((left ? X0 : XR0) >> 2) + w;  // X0, XR0 are multiples of 4
     t.kw = left ? kLW : kRW;
-    t.off = half * 2 * kRB * kRowWords + (left ? 0 : 4 * kLW) + w;
+    t.off = half * 2 * kRB * kSlotWords + pl * kRowWords + (left ? 0 : 4 * kLW) + w;
     return t;
   };
+  static_assert((RING2 ? 2 : 1) * kRB * NPL * kChunks <= 2 * kDenseThreads, "two staging tasks per thread");
+  constexpr bool kTwoTasks = (RING2 ? 2 : 1) * kRB * NPL * kChunks > kDenseThreads;
   const StageTask task_a = make_task(tid), task_b = make_task(kDenseThreads + tid);
   const int nr = th + 2 * kRB;  // !RING2: ring depth
-  int stage_slot = task_a.row;  // !RING2: ring slot of this thread's row in the next block to stage
-  auto run_task = [&](const StageTask& t, int row_begin) {
+  int stage_slot_a = task_a.row, stage_slot_b = task_b.row;  // !RING2: ring slot of the task's row in the next block to stage
+  auto run_task = [&](const StageTask& t, int row_begin, int stage_slot) {
     const int r = row_begin + t.row, gr = r - t.back;
     if (!t.on || r >= rows_in || gr < 0) return;
     const uint32_t* gp = t.g + (long long)gr * row_words;
     uint32_t w[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) w[k] = __ldg(gp + min(max(t.gb + k, 0), row_words - 1));
-    uint32_t* dst = s_ring + (size_t)(RING2 ? (r & (2 * kRB - 1)) : stage_slot) * kRowWords + t.off;
+    uint32_t* dst = s_ring + (size_t)(RING2 ? (r & (2 * kRB - 1)) : stage_slot) * kSlotWords + t.off;
     *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
 #pragma unroll
     for (int c = 1; c < 4; ++c)
@@ -169,9 +182,12 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
                      __funnelshift_r(w[2], w[3], 8 * c), __funnelshift_r(w[3], w[4], 8 * c));
   };
   auto stage = [&](int row_begin) {
-    run_task(task_a, row_begin);
-    if (RING2) run_task(task_b, row_begin);
-    else { stage_slot += kRB; if (stage_slot >= nr) stage_slot -= nr; }
+    run_task(task_a, row_begin, stage_slot_a);
+    if (kTwoTasks) run_task(task_b, row_begin, stage_slot_b);
+    if (!RING2) {
+      stage_slot_a += kRB; if (stage_slot_a >= nr) stage_slot_a -= nr;
+      stage_slot_b += kRB; if (stage_slot_b >= nr) stage_slot_b -= nr;
+    }
   };
 
   // this thread's operand words inside a ring row: L words [8ul, 8ul+8) of copy p; R words
@@ -183,8 +199,8 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const bool b4 = (dl >> 2) & 1, b3 = (dl >> 1) & 1, b2 = dl & 1;
   uint32_t* my_best = s_best + p * 32 + 8 * ul + own_i;
 
-  const uint32_t* my_lo = my_l + (RING2 ? 2 * kRB * kRowWords : 0);  // RING2: the half that holds the leaving rows
-  const uint32_t* my_ro = my_r + (RING2 ? 2 * kRB * kRowWords : 0);
+  const uint32_t* my_lo = my_l + (RING2 ? 2 * kRB * kSlotWords : 0);  // RING2: the half that holds the leaving rows
+  const uint32_t* my_ro = my_r + (RING2 ? 2 * kRB * kSlotWords : 0);
   int slot_new = 0, slot_old = 0;  // !RING2
 
   // one row of the band: the row enters the windows (V += h), the row th above leaves them (V -= h), the
@@ -196,31 +212,56 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
     {
       const int slot = RING2 ? (row & (2 * kRB - 1)) : slot_new;
       if (!RING2) slot_new = slot_new + 1 == nr ? 0 : slot_new + 1;
-      const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot * kRowWords);
-      const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot * kRowWords);
-      const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
-      const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-      const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int pl = 0; pl < NPL; ++pl) {
+        const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot * kSlotWords + pl * kRowWords);
+        const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot * kSlotWords + pl * kRowWords);
+        const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
+      }
     }
     if (HAS_OLD) {
       const int slot = RING2 ? (row & (2 * kRB - 1)) : slot_old;
       if (!RING2) slot_old = slot_old + 1 == nr ? 0 : slot_old + 1;
-      const uint4* lo = reinterpret_cast<const uint4*>(my_lo + (size_t)slot * kRowWords);
-      const uint4* ro = reinterpret_cast<const uint4*>(my_ro + (size_t)slot * kRowWords);
-      const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
-      const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+      if (NPL == 1) {
+        const uint4* lo = reinterpret_cast<const uint4*>(my_lo + (size_t)slot * kSlotWords);
+        const uint4* ro = reinterpret_cast<const uint4*>(my_ro + (size_t)slot * kSlotWords);
+        const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
+        const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
-          V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
+          for (int j = 0; j < NJ; ++j) {
+            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
+            V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
+          }
+      } else {
+        // colour: the leaving row's |a - b| of all planes go through one temporary, so the subtraction costs one IMAD per
+        // candidate slot whatever the number of planes
+        uint32_t T[8][NJ];
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          const uint4* lo = reinterpret_cast<const uint4*>(my_lo + (size_t)slot * kSlotWords + pl * kRowWords);
+          const uint4* ro = reinterpret_cast<const uint4*>(my_ro + (size_t)slot * kSlotWords + pl * kRowWords);
+          const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
+          const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) T[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], pl == 0 ? 0u : T[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) V[i][j] = imad_u32(T[i][j], minus_one, V[i][j]);
+      }
     }
     if (HAS_KEYS) {
       uint32_t best[8];
@@ -309,8 +350,8 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
 // NW = tw / 4 packed words per window (2..8: the halo columns come from one neighbouring lane).
-template <int DIR, int NW, bool RING2>
-__global__ void __launch_bounds__(kDenseThreads, 4)
+template <int DIR, int NW, bool RING2, int NPL>
+__global__ void __launch_bounds__(kDenseThreads, NPL == 1 ? 4 : 3)
 dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* s_ring = smem_u32;                                  // RING2 ? [2][2*kRB][kRowWords] : [th + 2*kRB][kRowWords]
@@ -333,8 +374,8 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   const int y0 = band * cfg.bh;
   const int bh = min(cfg.bh, J.nyc - y0);
   const int rows_in = bh + J.th - 1;
-  const uint32_t* Lg = reinterpret_cast<const uint32_t*>(J.left + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
-  const uint32_t* Rg = reinterpret_cast<const uint32_t*>(J.right + (long long)pair * J.frame_stride + (long long)y0 * J.row_stride);
+  const uint32_t* Lg = reinterpret_cast<const uint32_t*>(cfg.lp + (long long)pair * cfg.pair_stride + (long long)y0 * cfg.pitch);
+  const uint32_t* Rg = reinterpret_cast<const uint32_t*>(cfg.rp + (long long)pair * cfg.pair_stride + (long long)y0 * cfg.pitch);
   const int xb = cfg.xb;
 
   for (int i = tid; i < bh * 128; i += kDenseThreads) s_best[i] = 0xffffffffu;
@@ -387,14 +428,14 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
     const int r_shift = DIR < 0 ? -((D0_mine - D0) >> 2) : ((D0_mine - D0) >> 2);
-    if (fold_pass) dense_pass<DIR, NW, true, RING2>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
-    else dense_pass<DIR, NW, false, RING2>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    if (fold_pass) dense_pass<DIR, NW, true, RING2, NPL>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    else dense_pass<DIR, NW, false, RING2, NPL>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
   }
   if (thin) {
     const int D0 = d_lo + 32 * n_pass;
     const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
     const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
-    dense_pass<DIR, NW, false, RING2, 1>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, ul, dbase, 0, rows_in, minus_one);
+    dense_pass<DIR, NW, false, RING2, NPL, 1>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, ul, dbase, 0, rows_in, minus_one);
   }
   __syncthreads();
 
@@ -409,7 +450,7 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     const uint32_t key = s_best[((size_t)yy * 4 + pp) * 32 + a];
     const int x = X0 + xo, y = y0 + yy;
     const long long w = (long long)y * J.nx + x;
-    const long long g = (long long)pair * J.n_templates + w;
+    const long long g = (long long)(cfg.pair0 + pair) * J.n_templates + w;
     if (key & 0x80000000u) {  // untouched (~0) or only invalid candidates
       write_result(J, g, (uint32_t)w, x, y, -1, 0xffffffffu, 0.0, __longlong_as_double(0x7ff0000000000000ll));
     } else {
@@ -427,13 +468,25 @@ static int ceil_log2(long long v) {
   return b;
 }
 
-cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const char** kernel_name, int* n_launches) {
+// usv_dense_corr.cu: interleaved colour frames -> planes [pair][plane][H][pitch] of both cameras
+cudaError_t launch_split_planes(const DevJob& J, int pair0, int np, uint8_t* dst_l, uint8_t* dst_r, int pitch, cudaStream_t st);
+
+static int dense_plane_pitch(const DevJob& J) { return ((J.width + 15) & ~15) + 16; }
+
+// scratch the colour sweep needs per pair (planes of both cameras); 0 for one-plane frames
+size_t dense_scratch_bytes_per_pair(const DevJob& J) {
+  return J.channels == 3 ? 2ull * 3 * J.height * dense_plane_pitch(J) : 0;
+}
+
+cudaError_t launch_dense(const DevJob& J, int n_pairs, void* d_scratch, size_t scratch_bytes, cudaStream_t st, const char** kernel_name,
+                         int* n_launches) {
   // coverage of the sliding-window kernels; everything else runs on the direct-form kernel
-  if (J.tx || J.channels != 1 || J.sx != 1 || J.sy != 1) return cudaErrorNotSupported;
+  *n_launches = 0;
+  if (J.tx || (J.channels != 1 && J.channels != 3) || J.sx != 1 || J.sy != 1) return cudaErrorNotSupported;
   if (J.cost_kind != USV_COST_SAD) return cudaErrorNotSupported;
   const int nw = J.tw / 4;
   if (J.tw % 4 != 0 || !(nw == 2 || nw == 3 || nw == 4 || nw == 6 || nw == 8) || J.th > 64) return cudaErrorNotSupported;
-  if (J.out.score) { /* score is 0 for integer kinds; write_result handles it */ }
+  const int npl = J.channels;
   DenseCfg cfg;
   cfg.stride_px = 4 * (32 - nw + 1);
   cfg.n_xtiles = (J.nxc + cfg.stride_px - 1) / cfg.stride_px;
@@ -444,23 +497,32 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
   const long long smax = 255ll * J.n_elems;
   if (ceil_log2(smax + 1) + cfg.xb > 31) return cudaErrorNotSupported;  // bit 31 marks invalid candidates
   // bands: as tall as shared memory allows (amortises the th-1 warm-up rows), but enough CTAs to fill 148 SMs
-  const int smem_budget = 56 * 1024;  // 4 CTAs / SM
-  const bool ring2 = J.th > 16;  // measured: the short double-fetched ring pays from 24-row templates on
-  cfg.ring_words = ring2 ? kRingWords : (J.th + 2 * kRB) * kRowWords;
+  const int smem_budget = npl == 1 ? 56 * 1024 : 75 * 1024;  // 4 CTAs / SM; colour: 3 (one more plane set of temporaries in registers)
+  const bool ring2 = npl > 1 || J.th > 16;  // measured: the short double-fetched ring pays from 24-row templates on
+  const int rb = npl == 1 ? 4 : 2;
+  cfg.ring_words = (ring2 ? 4 * rb : J.th + 2 * rb) * npl * kRowWords;
   int bh_max = (smem_budget - cfg.ring_words * 4) / 512;
   if (bh_max < 8) return cudaErrorNotSupported;
+  const int ctas_per_sm = npl == 1 ? 4 : 3;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
-  while ((long long)n_bands * cfg.n_xtiles * n_pairs < g_sm_count * 3 && n_bands < (J.nyc + 15) / 16) ++n_bands;
+  while ((long long)n_bands * cfg.n_xtiles * n_pairs < g_sm_count * (ctas_per_sm - 1) && n_bands < (J.nyc + 15) / 16) ++n_bands;
   cfg.bh = (J.nyc + n_bands - 1) / n_bands;
   cfg.n_bands = (J.nyc + cfg.bh - 1) / cfg.bh;
   const size_t smem = (size_t)cfg.ring_words * 4 + (size_t)cfg.bh * 512;
-  cfg.n_pairs = n_pairs;
-  cfg.chunk_pairs = (int)std::min<long long>(64, std::max<long long>(1, (48ll << 20) / (2ll * J.height * J.row_stride)));
-  if ((long long)cfg.n_xtiles * cfg.n_bands * n_pairs > 0x7fffffffll) return cudaErrorNotSupported;
-  dim3 grid(cfg.n_xtiles * cfg.n_bands * n_pairs), block(kDenseThreads);
+  const int pitch = npl == 1 ? J.row_stride : dense_plane_pitch(J);
+  cfg.pitch = pitch;
+  cfg.plane_stride = npl == 1 ? 0 : (long long)J.height * pitch;
+  cfg.pair_stride = npl == 1 ? J.frame_stride : cfg.plane_stride * npl;
+  cfg.chunk_pairs = (int)std::min<long long>(64, std::max<long long>(1, (48ll << 20) / (2ll * npl * J.height * pitch)));
+  // colour: the planes of a chunk of pairs live in the caller's scratch
+  const size_t per_pair = dense_scratch_bytes_per_pair(J);
+  if (npl > 1 && (!d_scratch || scratch_bytes < per_pair)) return cudaErrorNotSupported;
+  const int launch_pairs = npl == 1 ? n_pairs : (int)std::min<size_t>((size_t)n_pairs, scratch_bytes / per_pair);
+  if ((long long)cfg.n_xtiles * cfg.n_bands * launch_pairs > 0x7fffffffll) return cudaErrorNotSupported;
 #define USV_DENSE_LAUNCH(D, NWW)                                                                          \
   {                                                                                                       \
-    auto kfn = ring2 ? dense_sad_argmin_kernel<D, NWW, true> : dense_sad_argmin_kernel<D, NWW, false>;                                                         \
+    auto kfn = npl == 3 ? dense_sad_argmin_kernel<D, NWW, true, 3>                                        \
+             : ring2 ? dense_sad_argmin_kernel<D, NWW, true, 1> : dense_sad_argmin_kernel<D, NWW, false, 1>; \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     if (e != cudaSuccess) return e;                                                                       \
     kfn<<<grid, block, smem, st>>>(J, cfg, 0xffffffffu);                                                  \
@@ -473,12 +535,30 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, cudaStream_t st, const ch
     case 6: USV_DENSE_LAUNCH(D, 6) break;                                                                 \
     default: USV_DENSE_LAUNCH(D, 8) break;                                                                \
   }
-  if (J.camera_side == USV_LEFT_CAM) { USV_DENSE_BY_NW(-1) } else { USV_DENSE_BY_NW(1) }
+  for (int p0 = 0; p0 < n_pairs; p0 += launch_pairs) {
+    const int np = std::min(launch_pairs, n_pairs - p0);
+    cfg.n_pairs = np;
+    cfg.pair0 = p0;
+    if (npl == 1) {
+      cfg.lp = J.left; cfg.rp = J.right;
+    } else {
+      uint8_t* pl_l = (uint8_t*)d_scratch;
+      uint8_t* pl_r = pl_l + (size_t)np * cfg.pair_stride;
+      cudaError_t e = launch_split_planes(J, p0, np, pl_l, pl_r, pitch, st);
+      if (e != cudaSuccess) return e;
+      cfg.lp = pl_l; cfg.rp = pl_r;
+      *n_launches += 2;
+    }
+    dim3 grid(cfg.n_xtiles * cfg.n_bands * np), block(kDenseThreads);
+    if (J.camera_side == USV_LEFT_CAM) { USV_DENSE_BY_NW(-1) } else { USV_DENSE_BY_NW(1) }
+    *n_launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
 #undef USV_DENSE_BY_NW
 #undef USV_DENSE_LAUNCH
   *kernel_name = "dense_sad_argmin_kernel";
-  *n_launches = 1;
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 
 }  // namespace usv

@@ -435,6 +435,17 @@ __global__ void corr_stats_kernel(const uint2* __restrict__ rs, int height, int 
   }
 }
 
+// for the colour SAD sweep of usv_dense.cu (kernels are launched from the translation unit that defines them)
+cudaError_t launch_split_planes(const DevJob& J, int pair0, int np, uint8_t* dst_l, uint8_t* dst_r, int pitch, cudaStream_t st) {
+  const long long plane_stride = (long long)J.height * pitch, pair_stride = plane_stride * J.channels;
+  const dim3 g((pitch + 255) / 256, J.height, np);
+  corr_planes_kernel<<<g, 256, 0, st>>>(J.left + (long long)pair0 * J.frame_stride, J.frame_stride, J.row_stride, J.width, J.height, J.channels, dst_l,
+                                        pair_stride, plane_stride, pitch);
+  corr_planes_kernel<<<g, 256, 0, st>>>(J.right + (long long)pair0 * J.frame_stride, J.frame_stride, J.row_stride, J.width, J.height, J.channels, dst_r,
+                                        pair_stride, plane_stride, pitch);
+  return cudaGetLastError();
+}
+
 size_t corr_scratch_bytes_per_pair(const DevJob& J, int* pitch_out) {
   const int pitch = ((J.width + 15) & ~15) + 16;
   if (pitch_out) *pitch_out = pitch;
