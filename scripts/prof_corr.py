@@ -6,6 +6,7 @@ import torch
 from unsynchronized_stereo_vision_proj325_b200 import _abi, api, synth
 n = 4
 ctx = api.Context(0)
+ctx.corr_kernel(sys.argv[1] if len(sys.argv) > 1 else "auto")
 left, right = synth.make_pairs(n, 1280, 720, 3, shift=37, noise_sigma=2.0)
 dl, dr = torch.from_numpy(np.ascontiguousarray(left)).cuda(), torch.from_numpy(np.ascontiguousarray(right)).cuda()
 f = _abi.frame_desc_for(left)

@@ -13,8 +13,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--c3-pairs", type=int, default=1)
 ap.add_argument("--c4-pairs", type=int, default=16)
 ap.add_argument("--only", default="")
+ap.add_argument("--corr-kernel", default="auto", help="auto | alu | mma | tcgen05 (Context.corr_kernel)")
 a = ap.parse_args()
 ctx = api.Context(0)
+ctx.corr_kernel(a.corr_kernel)
 st = torch.cuda.current_stream().cuda_stream
 
 

@@ -1,5 +1,5 @@
 // usv_dense_umma.cu — the correlation sweep of usv_dense_mma.cu with the row products on tcgen05 (UMMA):
-// tcgen05.mma.cta_group::1.kind::i8, M = 128 windows, N = 192 candidate columns, K = 32 bytes of one plane row, u8 x u8 -> s32
+// tcgen05.mma.cta_group::1.kind::i8, M = 128 windows, N = 128 or 192 candidate columns, K = 32 bytes of one plane row, u8 x u8 -> s32
 // accumulators in tensor memory. Measured rate of the instruction on B200: 8 192 MAC/clk/SM, 4.2x mma.sync
 // (scripts/dev/tcgen05_i8_probe.cu, which also pins the operand layout used here).
 //
@@ -17,8 +17,12 @@
 // Structure: no warp specialisation; per row one thread issues the 3 + 3 MMAs of the row (tiles staged during the previous
 // row) and commits to an mbarrier, everybody builds the tiles of the next row in the other buffer while the tensor pipe
 // works, waits (one lane per warp polls), and scores (chunks of 8 columns; chunks outside the warp's candidates are
-// skipped); one __syncthreads per row. One CTA per SM (1024 threads = 4 TMEM lane groups x 8 column parts, all 512 TMEM
-// columns). Opt-in with USV_CORR_UMMA=1 until it has earned the default.
+// skipped); one __syncthreads per row. Two shapes (below): one plane — N = 128, two CTAs of 512 threads per SM; three
+// planes — N = 192, one CTA of 1024 threads. The automatic dispatch (usv_dense_corr.cu) uses this kernel for one-plane
+// NCC / ZNCC on frames at least 128 windows wide, where it is the fastest sweep (7.7 k pairs/s on 640x480 gray against
+// 6.9 k for mma.sync); usv_set_option(USV_OPT_CORR_KERNEL, USV_CORR_KERNEL_TCGEN05) runs it wherever it applies. A
+// warp-specialised version (producer / issuer / scoring warps on mbarriers) was built and measured in round 2 and is
+// slower — scripts/dev/usv_dense_umma_warp_specialised_attempt.cu.txt records it and why.
 #include <algorithm>
 #include <cstdlib>
 
