@@ -40,8 +40,11 @@ namespace usv {
 
 constexpr int kDenseThreads = 128;
 constexpr int kLW = 32;         // words per L copy row (128 B)
-constexpr int kRW = 44;         // words per R copy row (40 used; 44 keeps the four copies on disjoint banks)
-constexpr int kRowWords = 4 * kLW + 4 * kRW;  // one ring row: 4 L copies + 4 R copies
+// JT = disparities per thread of a regular pass (4: 32 per warp; 8: 64 per warp, the colour sweep — twice the VABSDIFF4 per
+// shared-memory operand word). Words per R copy row: 24 + 2 JT + 8 used (40 / 48); 44 / 52 keep the four copies on disjoint banks.
+constexpr int r_copy_words(int jt) { return jt == 4 ? 44 : 52; }
+constexpr int r_copy_chunks(int jt) { return (32 + 2 * jt) / 4; }   // 16-byte chunks of the R segment staged per row: 10 / 12
+constexpr int row_words(int jt) { return 4 * kLW + 4 * r_copy_words(jt); }  // one ring row: 4 L copies + 4 R copies
 constexpr int kCodeOff = 32;    // candidate code = x0 -/+ d + kCodeOff: a valid candidate of column i has x0 -/+ d >= -4i >= -28
 
 struct DenseCfg {
@@ -80,7 +83,7 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // i0-1, i0-1-NW, ... and i1+NW-1, i1+2NW-1, ... start at BIG = 2^(31-xb) instead of 0. Every invalid
 // window then contains exactly one BIG column and its key carries bit 31 (true keys stay below 2^31,
 // checked on the host), every valid window contains none. No per-element masks, no second code path.
-template <int DIR, int NW, bool FOLD, bool RING2, int NPL, int NJ = 4>
+template <int DIR, int NW, bool FOLD, bool RING2, int NPL, int JT, int NJ = JT>
 __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg, uint32_t* s_ring, uint32_t* s_best,
                                            const uint32_t* __restrict__ Lg, const uint32_t* __restrict__ Rg, const int X0,
                                            const int XR0, const int run, const int dbase, const int r_shift,
@@ -92,6 +95,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const int x0 = X0 + p + 32 * ul;  // window x of this thread's column i = 0 (x_i = x0 + 4i, i < 8)
   const bool guest = FOLD && (lane & 3) == 0;
   constexpr int kRB = NPL == 1 ? 4 : 2;  // rows per staging block (a ring slot holds NPL plane rows)
+  constexpr int kRW = r_copy_words(JT), kRowWords = row_words(JT);
   constexpr int kSlotWords = NPL * kRowWords;
   const int th = J.th;
   const int row_words = cfg.pitch >> 2;
@@ -100,7 +104,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   const uint32_t minus_scale = key_scale * minus_one;  // -(1 << xb), kept opaque so the multiply stays an IMAD
   const uint32_t big = 1u << (31 - cfg.xb);
 
-  // NJ = 4: the regular pass (4 disparities per thread, 32 per warp). NJ = 1: the thin pass that closes a bounded range
+  // NJ = JT: the regular pass (JT disparities per thread, 8 JT per warp). NJ = 1 (JT = 4 only): the thin pass that closes a bounded range
   // (only j = 0 is computed; lanes jh = 0 carry the four disparities D0 + p - 3 .. D0 + p the regular passes of this
   // warp have not reached, lanes jh = 1 lie beyond dmax and are planted BIG) at about a third of a regular pass
   uint32_t code[NJ];
@@ -135,7 +139,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   // A block is 18 chunks of 4 words per row (8 of the L segment, 10 of the R segment), per half: thread t takes
   // task t (RING2: threads 0..15 also task 128 + t). A task turns five aligned global words into the four
   // byte-shifted copies of its chunk: 12 funnel shifts, one STS.128 per copy.
-  constexpr int kChunks = kLW / 4 + 10;
+  constexpr int kChunks = kLW / 4 + r_copy_chunks(JT);
   struct StageTask {
     const uint32_t* g;  // frame rows of the band (L or R), this task's plane
     int row, back;      // row inside the block; th for the leaving half, 0 for the entering half
@@ -193,7 +197,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
   // this thread's operand words inside a ring row: L words [8ul, 8ul+8) of copy p; R words
   // [rbase, rbase+12) of copy q, element (i, j) at rbase + (DIR<0 ? i - j + 4 : i + j)
   const uint32_t* my_l = s_ring + p * kLW + 8 * ul;
-  const uint32_t* my_r = s_ring + 4 * kLW + q * kRW + 8 * ul + (DIR < 0 ? 4 - 4 * jh : 4 * jh) + r_shift;
+  const uint32_t* my_r = s_ring + 4 * kLW + q * kRW + 8 * ul + (DIR < 0 ? JT - JT * jh : JT * jh) + r_shift;
   // the window this lane owns after the reduce-scatter min: position 8*ul + own_i
   const int own_i = ((dl >> 2) & 1) * 4 + ((dl >> 1) & 1) * 2 + (dl & 1);
   const bool b4 = (dl >> 2) & 1, b3 = (dl >> 1) & 1, b2 = dl & 1;
@@ -216,13 +220,15 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
       for (int pl = 0; pl < NPL; ++pl) {
         const uint4* lp = reinterpret_cast<const uint4*>(my_l + (size_t)slot * kSlotWords + pl * kRowWords);
         const uint4* rp = reinterpret_cast<const uint4*>(my_r + (size_t)slot * kSlotWords + pl * kRowWords);
-        const uint4 l0 = lp[0], l1 = lp[1], r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        const uint4 l0 = lp[0], l1 = lp[1];
         const uint32_t Lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        const uint32_t Rw[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+        uint32_t Rw[JT + 8];
+#pragma unroll
+        for (int k = 0; k < (JT + 8) / 4; ++k) { const uint4 rr = rp[k]; Rw[4 * k] = rr.x; Rw[4 * k + 1] = rr.y; Rw[4 * k + 2] = rr.z; Rw[4 * k + 3] = rr.w; }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], V[i][j]);
+          for (int j = 0; j < NJ; ++j) V[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + JT : i + j], V[i][j]);
       }
     }
     if (HAS_OLD) {
@@ -231,36 +237,50 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
       if (NPL == 1) {
         const uint4* lo = reinterpret_cast<const uint4*>(my_lo + (size_t)slot * kSlotWords);
         const uint4* ro = reinterpret_cast<const uint4*>(my_ro + (size_t)slot * kSlotWords);
-        const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
+        const uint4 m0 = lo[0], m1 = lo[1];
         const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+        uint32_t Rw[JT + 8];
+#pragma unroll
+        for (int k = 0; k < (JT + 8) / 4; ++k) { const uint4 rr = ro[k]; Rw[4 * k] = rr.x; Rw[4 * k + 1] = rr.y; Rw[4 * k + 2] = rr.z; Rw[4 * k + 3] = rr.w; }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], 0u);
+            const uint32_t t = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + JT : i + j], 0u);
             V[i][j] = imad_u32(t, minus_one, V[i][j]);  // V -= t on the FMA pipe
           }
       } else {
-        // colour: the leaving row's |a - b| of all planes go through one temporary, so the subtraction costs one IMAD per
-        // candidate slot whatever the number of planes
-        uint32_t T[8][NJ];
+        uint32_t T[8][NJ <= 4 ? NJ : 1];
+        // colour: with 4 disparities per thread the leaving row's |a - b| of all planes go through one temporary, so the
+        // subtraction costs one IMAD per candidate slot whatever the number of planes; with 8 (64 accumulators) there are
+        // no registers for the temporary and every plane subtracts on its own
 #pragma unroll
         for (int pl = 0; pl < NPL; ++pl) {
           const uint4* lo = reinterpret_cast<const uint4*>(my_lo + (size_t)slot * kSlotWords + pl * kRowWords);
           const uint4* ro = reinterpret_cast<const uint4*>(my_ro + (size_t)slot * kSlotWords + pl * kRowWords);
-          const uint4 m0 = lo[0], m1 = lo[1], s0 = ro[0], s1 = ro[1], s2 = ro[2];
+          const uint4 m0 = lo[0], m1 = lo[1];
           const uint32_t Lw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-          const uint32_t Rw[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+          uint32_t Rw[JT + 8];
+#pragma unroll
+          for (int k = 0; k < (JT + 8) / 4; ++k) { const uint4 rr = ro[k]; Rw[4 * k] = rr.x; Rw[4 * k + 1] = rr.y; Rw[4 * k + 2] = rr.z; Rw[4 * k + 3] = rr.w; }
+          if (NJ <= 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) T[i][NJ <= 4 ? j : 0] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + JT : i + j], pl == 0 ? 0u : T[i][NJ <= 4 ? j : 0]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < NJ; ++j) V[i][j] = imad_u32(sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + JT : i + j], 0u), minus_one, V[i][j]);
+          }
+        }
+        if (NJ <= 4) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) T[i][j] = sad4_acc(Lw[i], Rw[DIR < 0 ? i - j + 4 : i + j], pl == 0 ? 0u : T[i][j]);
+            for (int j = 0; j < NJ; ++j) V[i][j] = imad_u32(T[i][NJ <= 4 ? j : 0], minus_one, V[i][j]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) V[i][j] = imad_u32(T[i][j], minus_one, V[i][j]);
       }
     }
     if (HAS_KEYS) {
@@ -350,9 +370,10 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
 // NW = tw / 4 packed words per window (2..8: the halo columns come from one neighbouring lane).
-template <int DIR, int NW, bool RING2, int NPL>
+template <int DIR, int NW, bool RING2, int NPL, int JT>
 __global__ void __launch_bounds__(kDenseThreads, NPL == 1 ? 4 : 3)
 dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
+  constexpr int PD = 8 * JT;  // disparities a warp covers per pass
   extern __shared__ __align__(16) uint32_t smem_u32[];
   uint32_t* s_ring = smem_u32;                                  // RING2 ? [2][2*kRB][kRowWords] : [th + 2*kRB][kRowWords]
   uint32_t* s_best = smem_u32 + cfg.ring_words;                 // [bh][4][32]
@@ -401,8 +422,8 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
     const int xl = max(X0 + 32 * r, 0), xh = min(min(X0 + 32 * r + 31, X0 + cfg.stride_px - 1), J.nxc - 1);
     int dh;
     if (DIR < 0) dh = min(J.dmax, xh); else dh = min(J.dmax, J.nxc - 1 - xl);
-    n_run[r] = (xh >= xl && dh >= d_lo) ? (dh - d_lo + 3) / 32 + 1 : 0;
-    if (n_run[r] > 0 && dh - d_lo > 32 * (n_run[r] - 1)) thin = false;  // the thin pass would not reach dh in every warp
+    n_run[r] = (xh >= xl && dh >= d_lo) ? (dh - d_lo + 3) / PD + 1 : 0;
+    if (n_run[r] > 0 && dh - d_lo > PD * (n_run[r] - 1)) thin = false;  // the thin pass would not reach dh in every warp
   }
   const int n_all = max(max(n_run[0], n_run[1]), max(n_run[2], n_run[3]));
 #pragma unroll
@@ -413,29 +434,29 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   // its lane-0 slot in a pass where run 0 is already done can host run 3 of one of the tile's last passes,
   // which then need not run at all.
   int n_fold = 0;
-  if (DIR < 0 && n_run[0] <= n_run[1] && n_run[1] <= n_run[2] && n_run[2] <= n_run[3] && n_run[3] - n_run[0] <= 3)
+  if (JT == 4 && DIR < 0 && n_run[0] <= n_run[1] && n_run[1] <= n_run[2] && n_run[2] <= n_run[3] && n_run[3] - n_run[0] <= 3)
     n_fold = min(n_run[1] - n_run[0], n_run[3] - n_run[2]);
   const int n_pass = n_all - n_fold - (thin ? 1 : 0);  // thin implies equal runs, i.e. no fold
 
   for (int pass = 0; pass < n_pass; ++pass) {
-    const int D0 = d_lo + 32 * pass;
+    const int D0 = d_lo + PD * pass;
     const bool fold_pass = pass >= n_run[0] && pass < n_run[0] + n_fold;
     const bool guest = fold_pass && ul == 0;
     const int run = guest ? 3 : ul;
-    const int D0_mine = guest ? d_lo + 32 * (n_all - 1 - (pass - n_run[0])) : D0;
+    const int D0_mine = guest ? d_lo + PD * (n_all - 1 - (pass - n_run[0])) : D0;
     // d of (this lane, j = 0); d_j = dbase + 4j, j < 4. dl = 4*jh + q: R copy q, upper/lower half of the 8 d-steps
-    const int dbase = D0_mine + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
+    const int dbase = D0_mine + 4 * JT * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
     // first byte of the R copies for this pass: R copy q word w = bytes [XR0 + q + 4w, +4)
-    const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
+    const int XR0 = DIR < 0 ? X0 - D0 - PD : X0 + D0;
     const int r_shift = DIR < 0 ? -((D0_mine - D0) >> 2) : ((D0_mine - D0) >> 2);
-    if (fold_pass) dense_pass<DIR, NW, true, RING2, NPL>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
-    else dense_pass<DIR, NW, false, RING2, NPL>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    if (fold_pass) dense_pass<DIR, NW, true, RING2, NPL, JT>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
+    else dense_pass<DIR, NW, false, RING2, NPL, JT>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, run, dbase, r_shift, rows_in, minus_one);
   }
   if (thin) {
-    const int D0 = d_lo + 32 * n_pass;
-    const int dbase = D0 + 16 * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
-    const int XR0 = DIR < 0 ? X0 - D0 - 32 : X0 + D0;
-    dense_pass<DIR, NW, false, RING2, NPL, 1>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, ul, dbase, 0, rows_in, minus_one);
+    const int D0 = d_lo + PD * n_pass;
+    const int dbase = D0 + 4 * JT * (dl >> 2) + (DIR < 0 ? (p - (dl & 3)) : ((dl & 3) - p));
+    const int XR0 = DIR < 0 ? X0 - D0 - PD : X0 + D0;
+    dense_pass<DIR, NW, false, RING2, NPL, JT, 1>(J, cfg, s_ring, s_best, Lg, Rg, X0, XR0, ul, dbase, 0, rows_in, minus_one);
   }
   __syncthreads();
 
@@ -500,7 +521,9 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, void* d_scratch, size_t s
   const int smem_budget = npl == 1 ? 56 * 1024 : 75 * 1024;  // 4 CTAs / SM; colour: 3 (one more plane set of temporaries in registers)
   const bool ring2 = npl > 1 || J.th > 16;  // measured: the short double-fetched ring pays from 24-row templates on
   const int rb = npl == 1 ? 4 : 2;
-  cfg.ring_words = (ring2 ? 4 * rb : J.th + 2 * rb) * npl * kRowWords;
+  // colour: 8 disparities per thread (64 per pass) when the range is wide enough to fill such passes
+  const int jt = npl == 3 && std::min(J.dmax, J.nxc - 1) - std::max(J.dmin, -(J.nxc - 1)) + 1 >= 48 ? 8 : 4;
+  cfg.ring_words = (ring2 ? 4 * rb : J.th + 2 * rb) * npl * row_words(jt);
   int bh_max = (smem_budget - cfg.ring_words * 4) / 512;
   if (bh_max < 8) return cudaErrorNotSupported;
   const int ctas_per_sm = npl == 1 ? 4 : 3;
@@ -521,8 +544,8 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, void* d_scratch, size_t s
   if ((long long)cfg.n_xtiles * cfg.n_bands * launch_pairs > 0x7fffffffll) return cudaErrorNotSupported;
 #define USV_DENSE_LAUNCH(D, NWW)                                                                          \
   {                                                                                                       \
-    auto kfn = npl == 3 ? dense_sad_argmin_kernel<D, NWW, true, 3>                                        \
-             : ring2 ? dense_sad_argmin_kernel<D, NWW, true, 1> : dense_sad_argmin_kernel<D, NWW, false, 1>; \
+    auto kfn = npl == 3 ? (jt == 8 ? dense_sad_argmin_kernel<D, NWW, true, 3, 8> : dense_sad_argmin_kernel<D, NWW, true, 3, 4>) \
+             : ring2 ? dense_sad_argmin_kernel<D, NWW, true, 1, 4> : dense_sad_argmin_kernel<D, NWW, false, 1, 4>; \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     if (e != cudaSuccess) return e;                                                                       \
     kfn<<<grid, block, smem, st>>>(J, cfg, 0xffffffffu);                                                  \
