@@ -371,7 +371,7 @@ __device__ __forceinline__ void dense_pass(const DevJob& J, const DenseCfg& cfg,
 // DIR = -1: LeftCam (x' = x - d); DIR = +1: RightCam (x' = x + d).
 // NW = tw / 4 packed words per window (2..8: the halo columns come from one neighbouring lane).
 template <int DIR, int NW, bool RING2, int NPL, int JT>
-__global__ void __launch_bounds__(kDenseThreads, NPL == 1 ? 4 : 3)
+__global__ void __launch_bounds__(kDenseThreads, NPL == 1 && JT == 4 ? 4 : 3)
 dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus_one) {
   constexpr int PD = 8 * JT;  // disparities a warp covers per pass
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -434,7 +434,8 @@ dense_sad_argmin_kernel(const DevJob J, const DenseCfg cfg, const uint32_t minus
   // its lane-0 slot in a pass where run 0 is already done can host run 3 of one of the tile's last passes,
   // which then need not run at all.
   int n_fold = 0;
-  if (JT == 4 && DIR < 0 && n_run[0] <= n_run[1] && n_run[1] <= n_run[2] && n_run[2] <= n_run[3] && n_run[3] - n_run[0] <= 3)
+  // (the guest's R words sit 24 - (PD / 4) m words from its host's, m = passes between the two: m <= 3 at PD = 32, m <= 1 at PD = 64)
+  if (DIR < 0 && n_run[0] <= n_run[1] && n_run[1] <= n_run[2] && n_run[2] <= n_run[3] && n_run[3] - n_run[0] <= (JT == 4 ? 3 : 2))
     n_fold = min(n_run[1] - n_run[0], n_run[3] - n_run[2]);
   const int n_pass = n_all - n_fold - (thin ? 1 : 0);  // thin implies equal runs, i.e. no fold
 
@@ -518,15 +519,18 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, void* d_scratch, size_t s
   const long long smax = 255ll * J.n_elems;
   if (ceil_log2(smax + 1) + cfg.xb > 31) return cudaErrorNotSupported;  // bit 31 marks invalid candidates
   // bands: as tall as shared memory allows (amortises the th-1 warm-up rows), but enough CTAs to fill 148 SMs
-  const int smem_budget = npl == 1 ? 56 * 1024 : 75 * 1024;  // 4 CTAs / SM; colour: 3 (one more plane set of temporaries in registers)
+  const bool wide_range = std::min(J.dmax, J.nxc - 1) - std::max(J.dmin, -(J.nxc - 1)) + 1 >= 48;
+  // 8 disparities per thread (64 per pass, 64 accumulators, three CTAs per SM) when the range is wide enough to fill such
+  // passes, gray and colour alike: 24 operand words for 64 VABSDIFF4 instead of 20 for 32, half the reduce-scatter, staging and
+  // barriers per candidate (measured on C2: 10.08 against 10.92 ms although the full-range triangle wastes more slots)
+  const int jt = wide_range ? 8 : 4;
+  const int smem_budget = (npl == 1 && jt == 4) ? 56 * 1024 : 75 * 1024;  // 4 CTAs / SM; colour: 3 (one more plane set of temporaries in registers)
   const bool ring2 = npl > 1 || J.th > 16;  // measured: the short double-fetched ring pays from 24-row templates on
   const int rb = npl == 1 ? 4 : 2;
-  // colour: 8 disparities per thread (64 per pass) when the range is wide enough to fill such passes
-  const int jt = npl == 3 && std::min(J.dmax, J.nxc - 1) - std::max(J.dmin, -(J.nxc - 1)) + 1 >= 48 ? 8 : 4;
   cfg.ring_words = (ring2 ? 4 * rb : J.th + 2 * rb) * npl * row_words(jt);
   int bh_max = (smem_budget - cfg.ring_words * 4) / 512;
   if (bh_max < 8) return cudaErrorNotSupported;
-  const int ctas_per_sm = npl == 1 ? 4 : 3;
+  const int ctas_per_sm = (npl == 1 && jt == 4) ? 4 : 3;
   int n_bands = (J.nyc + bh_max - 1) / bh_max;
   while ((long long)n_bands * cfg.n_xtiles * n_pairs < g_sm_count * (ctas_per_sm - 1) && n_bands < (J.nyc + 15) / 16) ++n_bands;
   cfg.bh = (J.nyc + n_bands - 1) / n_bands;
@@ -545,6 +549,7 @@ cudaError_t launch_dense(const DevJob& J, int n_pairs, void* d_scratch, size_t s
 #define USV_DENSE_LAUNCH(D, NWW)                                                                          \
   {                                                                                                       \
     auto kfn = npl == 3 ? (jt == 8 ? dense_sad_argmin_kernel<D, NWW, true, 3, 8> : dense_sad_argmin_kernel<D, NWW, true, 3, 4>) \
+             : jt == 8 ? (ring2 ? dense_sad_argmin_kernel<D, NWW, true, 1, 8> : dense_sad_argmin_kernel<D, NWW, false, 1, 8>) \
              : ring2 ? dense_sad_argmin_kernel<D, NWW, true, 1, 4> : dense_sad_argmin_kernel<D, NWW, false, 1, 4>; \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     if (e != cudaSuccess) return e;                                                                       \
