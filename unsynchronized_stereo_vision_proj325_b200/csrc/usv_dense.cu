@@ -9,14 +9,18 @@
 // so a candidate costs ~2 VABSDIFF4 + ~3 integer adds instead of tw*th/4 VABSDIFF4.
 //
 // Mapping. A CTA owns an x-tile (116 px for 16-px templates) x a band of output rows of one
-// frame pair and walks the disparity range in passes of 32. Its four warps are the four byte
+// frame pair and walks the disparity range in passes of 8 * JT disparities. Its four warps are the four byte
 // phases p = x mod 4 (packed-byte operands must be word aligned, so the shared-memory ring
 // holds four byte-shifted copies of the L rows and of the R rows). Inside a warp 4 lanes run
-// along x (8 window positions each) and 8 lanes along d (4 disparities each, 4 apart; the lane's
-// R copy q fixes d mod 4): 32 V accumulators per thread. Window sums need the next x-lane's
-// first columns: three width-4 shuffles per disparity. Keys pack (cost << XB | candidate code)
-// so that "smallest cost, then smallest x'" (P/Main.cpp:451: an equal later candidate never
-// replaces) is one unsigned min whatever the reduction order; the key of the next window is
+// along x (8 window positions each) and 8 lanes along d (JT disparities each, 4 apart; the lane's
+// R copy q fixes d mod 4): 8 * JT V accumulators per thread. JT = 8 (64 accumulators, 64-disparity passes,
+// three CTAs per SM) serves ranges of 48 disparities and more: per thread and row the operand loads (24 words
+// for 64 VABSDIFF4), the reduce-scatter, the first key, staging and barriers are paid once for twice the
+// candidates; JT = 4 (32 accumulators, four CTAs per SM) serves narrow ranges. Interleaved colour frames are
+// split into planes and every plane is swept into the same accumulators (NPL = 3).
+// Window sums need the next x-lane's first columns: three width-4 shuffles per disparity. Keys pack
+// (cost << XB | candidate code) so that "smallest cost, then smallest x'" (P/Main.cpp:451: an equal later
+// candidate never replaces) is one unsigned min whatever the reduction order; the key of the next window is
 // slid from the previous one with two IMADs. A reduce-scatter min over the 8 d-lanes leaves
 // each lane with one window of the row, merged into the CTA's running best in shared memory.
 // After the last pass the CTA decodes its keys and writes Match records / disparity / distance
