@@ -475,3 +475,54 @@ def test_distance_lut_matches_epilogue(ctx, oracle):
     d = got["disparity_u16"][0]
     ok = d != _abi.NO_DISPARITY
     assert np.array_equal(got["distance"][0][ok], ctx.distance_lut(_abi.DIST_PINHOLE, 128)[d[ok]])  # same table, bit for bit
+
+
+@pytest.mark.parametrize("cost", ["sad", "zncc"])
+def test_block_search_host_is_generate_resolve_distance(ctx, oracle, cost):
+    """usv_block_search_host = the reference's call order (P/Main.cpp:1115-1143, :681-694) in one call: equal, entry for entry,
+    to the reference's own ResolveMatchList (compiled verbatim) over the oracle's accepted winners, with each entry's distance."""
+    left, right = synth.make_pairs(1, 150, 36, 1, shift=9, noise_sigma=2.0, seed=5)
+    left[0, :, 100:] = 60  # a flat region: many windows claim the same candidate
+    p = _abi.make_params(tmpl_w=12, tmpl_h=12, cost=cost, search_max=60, distance_kind=_abi.DIST_POWERLAW)
+    got_m, got_d = ctx.block_search(left[0], right[0], p)
+    exp = oracle.match_dense(left, right, p)
+    win = exp["matches"][0]
+    kept = win[win["RightIndex"] != _abi.NO_MATCH]
+    exp_list = oracle.ref_resolve_match_list(kept)
+    assert got_m.tobytes() == exp_list.tobytes()
+    exp_d = exp["distance"][0][exp_list["LeftIndex"]]
+    assert np.array_equal(np.isinf(got_d), np.isinf(exp_d))
+    fin = np.isfinite(exp_d)
+    assert np.allclose(got_d[fin], exp_d[fin], rtol=DIST_RTOL, atol=0)
+    assert len(got_m) < len(kept) or len(np.unique(kept["RightIndex"])) == len(kept)
+
+
+def test_stream_submit_io_lands_in_caller_arrays(ctx, oracle):
+    """usv_stream_submit_io: frames from and results into caller-owned (page-locked) arrays, disjoint slices per submission."""
+    left, right = synth.make_pairs(6, 160, 40, 1, shift=11, noise_sigma=2.0, seed=8)
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad", search_max=63)
+    f = _abi.frame_desc_for(left)
+    nx, ny, _ = api.grid_dims(f, p)
+    mask = _abi.OUT_RESOLVED_DISPARITY_U16 | _abi.OUT_RAW_COST_U16
+    res = np.zeros((6, nx * ny), np.uint16)
+    cost = np.zeros((6, nx * ny), np.uint16)
+    for a in (left, right, res, cost):
+        ctx.host_register(a)
+    st = ctx.stream(f, p, pairs_per_slot=2, n_slots=2, mask=mask)
+    try:
+        for k in range(3):
+            slot = k % 2
+            if k >= 2:
+                st.wait(slot)
+            st.submit_io(slot, left[2 * k:2 * k + 2], right[2 * k:2 * k + 2],
+                         {"resolved_disparity_u16": res[2 * k:2 * k + 2], "raw_cost_u16": cost[2 * k:2 * k + 2]})
+        st.wait(0)
+        st.wait(1)
+    finally:
+        st.close()
+        for a in (left, right, res, cost):
+            ctx.host_unregister(a)
+    ref = ctx.match_dense(left, right, p, mask=mask)
+    assert np.array_equal(res, ref["resolved_disparity_u16"]) and np.array_equal(cost, ref["raw_cost_u16"])
+    exp = oracle.match_dense(left, right, p, mask=_abi.OUT_RAW_COST)
+    assert np.array_equal(cost.astype(np.uint32), exp["raw_cost"])

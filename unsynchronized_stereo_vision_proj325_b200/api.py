@@ -184,6 +184,21 @@ class Context:
             out["cost_rows"], out["score_rows"] = cost_rows, score_rows
         return out
 
+    def block_search(self, left, right, params):
+        """One frame pair through the reference's call order on the device (usv_block_search_host): dense sweep -> the
+        whole-list ResolveMatchList -> distance of every surviving record. left/right: [H, W(, C)] uint8.
+        Returns (TentativeMatch as a MATCH_DTYPE array, distances f64)."""
+        assert left.shape == right.shape and left.strides == right.strides
+        f = _abi.frame_desc_for(left[None])
+        nx, ny, _ = grid_dims(f, params)
+        cap = nx * ny
+        m = np.zeros(cap, _abi.MATCH_DTYPE)
+        d = np.zeros(cap, np.float64)
+        n = C.c_int64()
+        rc = lib().usv_block_search_host(self._h, _ptr(left), _ptr(right), C.byref(f), C.byref(params), _ptr(m), _ptr(d), C.c_int64(cap), C.byref(n))
+        self._check(rc, "usv_block_search_host")
+        return m[:n.value], d[:n.value]
+
     # ---- device-pointer entry point (inputs resident in HBM) ------------------
     def match_dense_device(self, d_left, d_right, frame, n_pairs, params, d_out, stream=0):
         """Raw device pointers (ints); asynchronous on `stream` (a cudaStream_t)."""
@@ -379,6 +394,19 @@ class Stream:
         self.ctx._check(lib().usv_stream_submit_gather(self._h, C.c_int32(slot), _ptr(left_store), _ptr(il), _ptr(right_store), _ptr(ir),
                                                        C.c_int64(left_store.shape[0]), C.byref(f), C.c_int32(len(il))),
                         "usv_stream_submit_gather")
+
+    def submit_io(self, slot, left, right, outs):
+        """Frames from, and results into, caller-owned host arrays (usv_stream_submit_io): `outs` maps output names of the
+        stream's mask to C-contiguous arrays [n, ny*nx] that receive this submission's results directly."""
+        f = _abi.frame_desc_for(left)
+        st = Outputs()
+        for name, bit, dt in _abi.OUTPUT_FIELDS:
+            if self.mask & bit:
+                a = outs[name]
+                assert a.dtype == dt and a.flags["C_CONTIGUOUS"]
+                setattr(st, name, a.ctypes.data)
+        self.ctx._check(lib().usv_stream_submit_io(self._h, C.c_int32(slot), _ptr(left), _ptr(right), C.byref(f), C.c_int32(left.shape[0]), C.byref(st)),
+                        "usv_stream_submit_io")
 
     def wait(self, slot):
         self.ctx._check(lib().usv_stream_wait(self._h, C.c_int32(slot)), "usv_stream_wait")
