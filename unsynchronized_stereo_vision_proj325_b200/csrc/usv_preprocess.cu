@@ -55,6 +55,21 @@ __device__ __forceinline__ void remap_pixel(const PreJob& J, const uint8_t* __re
   int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
   if (w00 == 32768) { w00 = 32767; w11 = 1; }
   const int sx = xy.x, sy = xy.y;
+  if ((unsigned)sx < (unsigned)(J.width - 1) && (unsigned)sy < (unsigned)(J.height - 1)) {
+    // all four taps inside the frame (every pixel but a border band): the weights factor, 32 * [(32 - fy) ((32 - fx) p00 + fx p01)
+    // + fy ((32 - fx) p10 + fx p11)] is the same integer as the sum of the four products, and the 32767 / +1 fix-up of the
+    // fx = fy = 0 case cannot change the result ((16384 - p00 + p11) >> 15 == 0 for bytes), so no special case either
+    const uint8_t* p0 = src + (long long)sy * J.src_stride + 3 * sx;
+    const uint8_t* p1 = p0 + J.src_stride;
+    const int wx1 = fx, wx0 = 32 - fx, wy1 = fy, wy0 = 32 - fy;
+    int t0[6], t1[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { t0[k] = __ldg(p0 + k); t1[k] = __ldg(p1 + k); }
+    b = (wy0 * (wx0 * t0[0] + wx1 * t0[3]) + wy1 * (wx0 * t1[0] + wx1 * t1[3]) + 512) >> 10;
+    g = (wy0 * (wx0 * t0[1] + wx1 * t0[4]) + wy1 * (wx0 * t1[1] + wx1 * t1[4]) + 512) >> 10;
+    r = (wy0 * (wx0 * t0[2] + wx1 * t0[5]) + wy1 * (wx0 * t1[2] + wx1 * t1[5]) + 512) >> 10;
+    return;
+  }
   int acc[3] = {1 << 14, 1 << 14, 1 << 14};
   auto tap = [&](int yy, int xx, int w) {
     if (w && yy >= 0 && yy < J.height && xx >= 0 && xx < J.width) {
@@ -66,12 +81,13 @@ __device__ __forceinline__ void remap_pixel(const PreJob& J, const uint8_t* __re
   b = acc[0] >> 15; g = acc[1] >> 15; r = acc[2] >> 15;
 }
 
-// cv::cvtColor BGR2HSV, 8-bit, H in [0, 180): integer arithmetic with 12-bit reciprocal tables (color_hsv)
-__device__ __forceinline__ uint32_t bgr2hsv_word(int b, int g, int r) {
+// cv::cvtColor BGR2HSV, 8-bit, H in [0, 180): integer arithmetic with 12-bit reciprocal tables (color_hsv). The tables are
+// indexed per thread: in constant memory divergent indices serialise, so every CTA keeps a copy in shared memory.
+__device__ __forceinline__ uint32_t bgr2hsv_word(int b, int g, int r, const int* __restrict__ sdiv, const int* __restrict__ hdiv) {
   const int v = max(max(b, g), r), diff = v - min(min(b, g), r);
-  const int s = (diff * c_sdiv[v] + (1 << 11)) >> 12;
+  const int s = (diff * sdiv[v] + (1 << 11)) >> 12;
   int h = v == r ? g - b : (v == g ? b - r + 2 * diff : r - g + 4 * diff);
-  h = (h * c_hdiv[diff] + (1 << 11)) >> 12;
+  h = (h * hdiv[diff] + (1 << 11)) >> 12;
   if (h < 0) h += 180;
   return (uint32_t)min(max(h, 0), 255) | (uint32_t)s << 8 | (uint32_t)v << 16;
 }
@@ -105,11 +121,14 @@ __device__ __forceinline__ void hsv2bgr_pixel(int hq, int sq, int vq, int flavou
     tab[2] = __fmul_rn(v, t2);
     tab[3] = __fmul_rn(v, t3);
   }
-  // sector_data = {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}}: (b, g, r) tab indices, two bits each, six bits per sector
-  constexpr unsigned long long kSectors = 0x0Dull | 0x21ull << 6 | 0x13ull << 12 | 0x18ull << 18 | 0x34ull << 24 | 0x06ull << 30;
-  const uint32_t e = (uint32_t)(kSectors >> (6 * sector));
-  auto q = [&](uint32_t k) { return min(max(__float2int_rn(__fmul_rn(tab[k & 3], 255.f)), 0), 255); };
-  b = q(e); g = q(e >> 2); r = q(e >> 4);
+  // sector_data = {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}}: (b, g, r) tab indices per sector, as selects (an
+  // indexed four-entry table would live in local memory or behind branches)
+  const float t0 = tab[0], t1 = tab[1], t2 = tab[2], t3 = tab[3];
+  const float fb = sector < 2 ? t1 : sector == 2 ? t3 : sector < 5 ? t0 : t2;
+  const float fg = sector == 0 ? t3 : sector < 3 ? t0 : sector == 3 ? t2 : t1;
+  const float fr = sector == 0 ? t0 : sector == 1 ? t2 : sector < 4 ? t1 : sector == 4 ? t3 : t0;
+  auto q = [&](float f) { return min(max(__float2int_rn(__fmul_rn(f, 255.f)), 0), 255); };
+  b = q(fb); g = q(fg); r = q(fr);
 }
 
 constexpr int kPreThreads = 256;
@@ -117,13 +136,15 @@ constexpr int kPrePix = 4;  // pixels per thread (consecutive in x): one 32-bit 
 
 // sweep 1 (lighting correction on): remap -> BGR2HSV -> HSV words + histogram of V
 __global__ void __launch_bounds__(kPreThreads) rectify_hsv_hist_kernel(const PreJob J) {
-  // eight copies of the histogram, picked by lane: neighbouring pixels have similar V, and shared-memory atomics
-  // on one address serialise
-  __shared__ uint32_t s_hist[256 * 8];
+  // 32 copies of the histogram, one per lane: bin v of lane l sits in bank l, so a warp's 32 atomics never collide on a bank
+  // or an address whatever the values (neighbouring pixels have similar V: fewer copies serialise)
+  __shared__ uint32_t s_hist[256 * 32];
+  __shared__ int s_sdiv[256], s_hdiv[256];
   const int frame = blockIdx.y;
-  for (int i = threadIdx.x; i < 256 * 8; i += kPreThreads) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < 256 * 32; i += kPreThreads) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < 256; i += kPreThreads) { s_sdiv[i] = c_sdiv[i]; s_hdiv[i] = c_hdiv[i]; }
   __syncthreads();
-  const uint32_t copy = threadIdx.x & 7;
+  const uint32_t copy = threadIdx.x & 31;
   const uint8_t* src = J.src + (long long)frame * J.src_frame_stride;
   uint32_t* hsv = J.hsv + (long long)frame * J.width * J.height;
   const uint32_t groups_per_row = (uint32_t)(J.width + kPrePix - 1) / kPrePix;
@@ -138,21 +159,37 @@ __global__ void __launch_bounds__(kPreThreads) rectify_hsv_hist_kernel(const Pre
       b[k] = g[k] = r[k] = 0;
       if (x0 + k < J.width) remap_pixel(J, src, x0 + k, y, b[k], g[k], r[k]);
     }
+    uint32_t w[kPrePix];
+#pragma unroll
+    for (int k = 0; k < kPrePix; ++k) w[k] = bgr2hsv_word(b[k], g[k], r[k], s_sdiv, s_hdiv);
+    uint32_t* o = hsv + (long long)y * J.width + x0;
+    if (x0 + kPrePix <= J.width && ((uintptr_t)o & 15) == 0) {
+      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPrePix; ++k)
+        if (x0 + k < J.width) o[k] = w[k];
+    }
+    // equal V in neighbouring pixels is the common case: one atomic per run of equal values
 #pragma unroll
     for (int k = 0; k < kPrePix; ++k) {
-      const int x = x0 + k;
-      if (x < J.width) {
-        const uint32_t w = bgr2hsv_word(b[k], g[k], r[k]);
-        hsv[(long long)y * J.width + x] = w;
-        atomicAdd(&s_hist[(w >> 16) * 8 + copy], 1u);
+      if (x0 + k >= J.width) continue;
+      const uint32_t v = w[k] >> 16;
+      uint32_t cnt = 1;
+      bool first = true;
+#pragma unroll
+      for (int q = 0; q < kPrePix; ++q) {
+        if (q == k || x0 + q >= J.width) continue;
+        if ((w[q] >> 16) == v) { if (q < k) first = false; else ++cnt; }
       }
+      if (first) atomicAdd(&s_hist[v * 32 + copy], cnt);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 256; i += kPreThreads) {
     uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) c += s_hist[i * 8 + k];
+    for (int k = 0; k < 32; ++k) c += s_hist[i * 32 + ((k + i) & 31)];  // rotated: the threads of a warp read distinct banks
     if (c) atomicAdd(&J.hist[frame * 256 + i], c);
   }
 }
@@ -202,11 +239,21 @@ __global__ void __launch_bounds__(kPreThreads) hsv_gray_kernel(const PreJob J) {
     const uint32_t yu = gi / groups_per_row;
     const int y = (int)yu, x0 = (int)(gi - yu * groups_per_row) * kPrePix;
     uint32_t packed = 0;
+    const uint32_t* hp = hsv + (long long)y * J.width + x0;
+    uint32_t w4[kPrePix] = {0, 0, 0, 0};
+    if (x0 + kPrePix <= J.width && ((uintptr_t)hp & 15) == 0) {
+      const uint4 q = *reinterpret_cast<const uint4*>(hp);
+      w4[0] = q.x; w4[1] = q.y; w4[2] = q.z; w4[3] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPrePix; ++k)
+        if (x0 + k < J.width) w4[k] = hp[k];
+    }
 #pragma unroll
     for (int k = 0; k < kPrePix; ++k) {
       const int x = x0 + k;
       if (x < J.width) {
-        const uint32_t w = hsv[(long long)y * J.width + x];
+        const uint32_t w = w4[k];
         int b, g, r;
         hsv2bgr_pixel(w & 255, (w >> 8) & 255, s_lut[w >> 16], J.flavour, b, g, r);
         packed |= (uint32_t)gray_of(b, g, r, J.flavour) << (8 * k);
