@@ -450,13 +450,21 @@ def main():
     # ---------------- the C++ drop-in (rank 0 drives every GPU of the run from one process) -----------
     cpp = None
     barrier()
-    if rank == 0 and os.path.exists(HOST_BIN):
-        try:
-            r = subprocess.run([HOST_BIN, "--bench", str(n * world), str(world), str(max(3, args.steps // 2)), "2"], capture_output=True, text=True, timeout=600)
-            cpp = json.loads(r.stdout.strip().splitlines()[-1])
-            cpp["value"], cpp["unit"] = cpp.pop("pairs_per_s"), "pairs/s"
-        except Exception as e:
-            cpp = {"unavailable": str(e)}
+    # the other ranks wait on the HOST (a key of the rendezvous store): a NCCL barrier would keep a spinning kernel on their
+    # GPUs, which the C++ workers are about to use
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
+    if rank == 0:
+        if os.path.exists(HOST_BIN):
+            try:
+                r = subprocess.run([HOST_BIN, "--bench", str(n * world), str(world), str(max(3, args.steps // 2)), "2"], capture_output=True, text=True, timeout=600)
+                cpp = json.loads(r.stdout.strip().splitlines()[-1])
+                cpp["value"], cpp["unit"] = cpp.pop("pairs_per_s"), "pairs/s"
+            except Exception as e:
+                cpp = {"unavailable": str(e)}
+        if store is not None:
+            store.set("usv_cpp_dropin_done", "1")
+    elif store is not None:
+        store.wait(["usv_cpp_dropin_done"])
     barrier()
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------------------------------------
@@ -542,7 +550,7 @@ def run_configs_block(args, ctx, rank, world, barrier, max_over_ranks, all_ranks
 
     # ---- C3: 1280x720 colour, 32x32 ZNCC, D = 256; 8 pairs per GPU resident in HBM
     try:
-        n3 = 8
+        n3 = 16
         l3, r3 = synth.make_pairs(n3, 1280, 720, 3, shift=60, noise_sigma=3.0, seed=33 + rank)
         p3 = _abi.make_params(tmpl_w=32, tmpl_h=32, cost="zncc", search_max=255)
         f3 = _abi.frame_desc_for(l3)
