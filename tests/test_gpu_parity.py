@@ -526,3 +526,48 @@ def test_stream_submit_io_lands_in_caller_arrays(ctx, oracle):
     assert np.array_equal(res, ref["resolved_disparity_u16"]) and np.array_equal(cost, ref["raw_cost_u16"])
     exp = oracle.match_dense(left, right, p, mask=_abi.OUT_RAW_COST)
     assert np.array_equal(cost.astype(np.uint32), exp["raw_cost"])
+
+
+def test_device_api_out_of_frame_template_is_no_match(ctx, oracle):
+    """a template list in HBM cannot be validated by the host; a template that does not fit the frame gets the
+    "no candidate" record instead of an out-of-bounds strip, and its neighbours in the list are unaffected."""
+    torch = pytest.importorskip("torch")
+    left, right = synth.make_pairs(1, 128, 32, 1, shift=7, noise_sigma=2.0, seed=4)
+    dl, dr = torch.from_numpy(np.ascontiguousarray(left)).cuda(), torch.from_numpy(np.ascontiguousarray(right)).cuda()
+    f = _abi.frame_desc_for(left)
+    p = _abi.make_params(tmpl_w=16, tmpl_h=16, cost="sad")
+    tx = torch.tensor([40, 113, -1, 60, 5000], dtype=torch.int32).cuda()   # 113 = nxc: one past the last valid x
+    ty = torch.tensor([3, 3, 3, 17, 3], dtype=torch.int32).cuda()          # 17 = nyc: one past the last valid y
+    o_ri = torch.zeros(5, dtype=torch.int32).cuda()
+    o_rc = torch.zeros(5, dtype=torch.int32).cuda()
+    out = _abi.Outputs()
+    out.right_index, out.raw_cost = o_ri.data_ptr(), o_rc.data_ptr()
+    ctx.match_templates_device(dl.data_ptr(), dr.data_ptr(), f, 1, tx.data_ptr(), ty.data_ptr(), 5, p, out, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ri = o_ri.cpu().numpy().view(np.uint32)
+    exp = oracle.match_templates(left, right, [40], [3], p, mask=_abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST)
+    assert ri[0] == exp["right_index"][0, 0] and o_rc.cpu().numpy().view(np.uint32)[0] == exp["raw_cost"][0, 0]
+    assert (ri[1:] == _abi.NO_MATCH).all()
+    assert api.lib().usv_device_status(ctx._h) == 0
+
+
+def test_destroy_refuses_while_a_stream_is_open():
+    """usv_destroy with a live usv_stream would leave the stream with a dangling context; it is refused instead,
+    and the Python Context closes its streams first."""
+    import ctypes as C
+    L = api.lib()
+    h = C.c_void_p()
+    assert L.usv_create(0, C.byref(h)) == 0
+    f = _abi.FrameDesc(64, 32, 1, 64, 64 * 32)
+    p = _abi.make_params(tmpl_w=8, tmpl_h=8, cost="sad")
+    s = C.c_void_p()
+    assert L.usv_stream_create(h, C.byref(f), C.byref(p), C.c_int32(2), C.c_int32(2), C.c_uint32(_abi.OUT_DISPARITY_U16), C.byref(s)) == 0
+    assert L.usv_destroy(h) == _abi.USV_ERR_INVALID_ARG
+    assert b"usv_stream" in L.usv_last_error(h)
+    L.usv_stream_destroy.argtypes = [C.c_void_p]
+    assert L.usv_stream_destroy(s) == 0
+    assert L.usv_destroy(h) == 0
+    c = api.Context(0)
+    st = c.stream(f, p, pairs_per_slot=2, n_slots=2, mask=_abi.OUT_DISPARITY_U16)
+    c.close()            # closes the stream first
+    assert st._h is None
