@@ -114,7 +114,9 @@ typedef struct usv_outputs {
   double *score;           /* NCC / ZNCC correlation of the winner            */
   double *distance;        /* cm, f64 (reference type)                        */
   float *distance_f32;     /* cm, f32 copy for bandwidth-bound consumers      */
-  uint16_t *disparity_u16; /* d of the winner or USV_NO_DISPARITY             */
+  uint16_t *disparity_u16; /* d of the winner or USV_NO_DISPARITY. Meant for search_min >= 0: a negative d
+                            * (candidate on the other side of the window) is stored modulo 2^16, and -1 then
+                            * reads as USV_NO_DISPARITY — take right_index or matches for such ranges */
   uint16_t *raw_cost_u16;  /* raw_cost as u16 (0xFFFF = no candidate): SAD only,
                               and only when 255*tmpl_w*tmpl_h*channels fits 16
                               bits (else USV_ERR_UNSUPPORTED); lossless        */

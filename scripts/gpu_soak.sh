@@ -1,5 +1,7 @@
+# Randomised parity soak against the CPU oracle on one B200 (bit-exact or it prints MISMATCH).   usage: bash scripts/gpu_soak.sh
 mkdir -p gpurun_out
-timeout 900 python scripts/stress_dense.py 1500 9001 > gpurun_out/soak_dense.log 2>&1; echo "dense exit $?"; tail -2 gpurun_out/soak_dense.log
-timeout 1200 python scripts/stress_corr.py 1200 9002 mma > gpurun_out/soak_corr_mma.log 2>&1; echo "corr mma exit $?"; tail -2 gpurun_out/soak_corr_mma.log
-timeout 900 python scripts/stress_corr.py 500 9003 > gpurun_out/soak_corr.log 2>&1; echo "corr exit $?"; tail -2 gpurun_out/soak_corr.log
-USV_CORR_MMA=0 timeout 900 python scripts/stress_corr.py 300 9004 > gpurun_out/soak_corr_alu.log 2>&1; echo "corr alu exit $?"; tail -1 gpurun_out/soak_corr_alu.log
+( time timeout 700 python scripts/stress_dense.py 1000 9101 ) > gpurun_out/soak_dense.log 2>&1; echo "dense exit $?"; tail -5 gpurun_out/soak_dense.log
+( time timeout 500 python scripts/stress_corr.py 600 9102 mma ) > gpurun_out/soak_corr_mma.log 2>&1; echo "corr mma exit $?"; tail -5 gpurun_out/soak_corr_mma.log
+( time timeout 400 python scripts/stress_corr.py 300 9103 ) > gpurun_out/soak_corr.log 2>&1; echo "corr exit $?"; tail -5 gpurun_out/soak_corr.log
+( time timeout 300 python scripts/stress_corr.py 200 9105 mma tcgen05 ) > gpurun_out/soak_corr_tcgen05.log 2>&1; echo "corr tcgen05 exit $?"; tail -5 gpurun_out/soak_corr_tcgen05.log
+( time timeout 300 python scripts/stress_corr.py 150 9104 all alu ) > gpurun_out/soak_corr_alu.log 2>&1; echo "corr alu exit $?"; tail -5 gpurun_out/soak_corr_alu.log

@@ -437,6 +437,8 @@ def _resolved_map_from_reference(oracle, got_pair, nx, use_ref):
     ("zncc", _abi.LEFT_CAM, 160, 30, 16, 16, dict(search_max=63)),
     ("ncc", _abi.RIGHT_CAM, 140, 26, 9, 7, dict(search_max=50, accept_threshold=0.3)),
     ("sad", _abi.LEFT_CAM, 96, 24, 11, 4, dict(stride_x=2, stride_y=3, search_max=40)),   # direct-form kernel
+    ("sad", _abi.LEFT_CAM, 120, 26, 8, 8, dict(search_min=-12, search_max=30)),           # negative disparities: resolved from RightIndex
+    ("ssd", _abi.RIGHT_CAM, 120, 26, 8, 8, dict(search_min=-20, search_max=25)),
 ])
 def test_resolved_disparity_map(ctx, oracle, cost, side, w, h, tw, th, kw):
     """usv_outputs.resolved_disparity_u16: ResolveMatchList (P/Main.cpp:432-477) over the dense winners on the device. Frames with

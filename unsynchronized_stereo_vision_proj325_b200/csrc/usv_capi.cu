@@ -392,14 +392,22 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
     if (!usv::resolve_rows_supported(J.nx, J.nxc)) return fail(ctx, USV_ERR_UNSUPPORTED, "resolved_disparity_u16: rows wider than 2048 windows");
     const bool integer = p->cost_kind <= USV_COST_SSD;
     const size_t n_res = (size_t)J.n_templates * n_pairs;
-    const bool have_int = integer && ((J.out.disparity_u16 && (J.out.raw_cost_u16 || J.out.raw_cost)) || (J.out.right_index && J.out.raw_cost));
+    // a u16 disparity names x' only when no candidate lies on the other side of the window (search_min >= 0): negative
+    // disparities are stored modulo 2^16 and -1 would read as USV_NO_DISPARITY; such ranges resolve from RightIndex
+    const bool disp_ok = p->search_min >= 0;
+    const bool have_int = integer && ((disp_ok && J.out.disparity_u16 && (J.out.raw_cost_u16 || J.out.raw_cost)) || (J.out.right_index && J.out.raw_cost));
     if (!have_int && !(J.out.matches && !integer)) {
       DevBuf& ws = win_ws ? *win_ws : ctx->win_ws;
-      if (integer) {  // disparity (2 B) + cost (4 B, or what the caller already asked for)
+      if (integer && disp_ok) {  // disparity (2 B) + cost (4 B, or what the caller already asked for)
         const bool need_cost = !J.out.raw_cost && !J.out.raw_cost_u16;
         if ((rc = grow(ctx, ws, n_res * (need_cost ? 6 : 2) + 16))) return rc;
         if (need_cost) J.out.raw_cost = (uint32_t*)ws.p;
         if (!J.out.disparity_u16) J.out.disparity_u16 = (uint16_t*)((uint32_t*)ws.p + (need_cost ? n_res : 0));
+      } else if (integer) {      // RightIndex (4 B) + cost (4 B)
+        const bool need_cost = !J.out.raw_cost, need_ri = !J.out.right_index;
+        if ((rc = grow(ctx, ws, n_res * 4 * ((need_cost ? 1 : 0) + (need_ri ? 1 : 0)) + 16))) return rc;
+        if (need_cost) J.out.raw_cost = (uint32_t*)ws.p;
+        if (need_ri) J.out.right_index = (uint32_t*)ws.p + (need_cost ? n_res : 0);
       } else {
         if ((rc = grow(ctx, ws, n_res * sizeof(usv_match)))) return rc;
         J.out.matches = (usv_match*)ws.p;
@@ -411,7 +419,7 @@ static int match_device(usv_ctx* ctx, const uint8_t* d_left, const uint8_t* d_ri
     const bool integer = p->cost_kind <= USV_COST_SSD;
     usv::ResolveRowsSrc S;
     memset(&S, 0, sizeof(S));
-    if (integer && J.out.disparity_u16 && (J.out.raw_cost_u16 || J.out.raw_cost)) {
+    if (integer && p->search_min >= 0 && J.out.disparity_u16 && (J.out.raw_cost_u16 || J.out.raw_cost)) {
       S.disparity_u16 = J.out.disparity_u16; S.raw_cost_u16 = J.out.raw_cost_u16; S.raw_cost = J.out.raw_cost;
     } else if (integer && J.out.right_index && J.out.raw_cost) {
       S.right_index = J.out.right_index; S.raw_cost = J.out.raw_cost;
