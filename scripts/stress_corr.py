@@ -44,6 +44,14 @@ for t in range(n_cases):
     g2 = ctx.match_dense(left, right, p, mask=_abi.OUT_MATCHES | _abi.OUT_DISPARITY_U16 | _abi.OUT_DISTANCE)
     ok = ok and g2["matches"].tobytes() == exp["matches"].tobytes() and np.array_equal(g2["disparity_u16"], exp["disparity_u16"])
     ok = ok and g2["distance"].tobytes() == got["distance"].tobytes()
+    if ok and t % 4 == 0:  # the resolved disparity map (device-side ResolveMatchList over f64 / integer values) against the oracle's restatement
+        g3 = ctx.match_dense(left, right, p, mask=_abi.OUT_MATCHES | _abi.OUT_DISPARITY_U16 | _abi.OUT_RESOLVED_DISPARITY_U16)
+        for k in range(n):
+            win = g3["matches"][k]
+            out = oracle.resolve_match_list(win[win["RightIndex"] != _abi.NO_MATCH])
+            alive = np.zeros(len(win), bool)
+            alive[np.unique(out["LeftIndex"])] = True
+            ok = ok and np.array_equal(g3["resolved_disparity_u16"][k], np.where(alive, g3["disparity_u16"][k], _abi.NO_DISPARITY).astype(np.uint16))
     if not ok:
         bad += 1
         nb = int((got["right_index"] != exp["right_index"]).sum())

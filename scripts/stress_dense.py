@@ -28,8 +28,9 @@ for t in range(n_cases):
     left, right = synth.make_pairs(n, w, h, c, shift=shift if abs(shift) < w else 0, noise_sigma=float(rng.choice([0, 2.0])), seed=1000 + t)
     if rng.random() < 0.15:
         left[:] = 128; right[:] = 128           # flat frames: every candidate ties, the first one must win
+    sx, sy = (int(rng.integers(1, 4)), int(rng.integers(1, 4))) if rng.random() < 0.1 else (1, 1)  # strided grids run on the direct-form kernel
     p = _abi.make_params(tmpl_w=tw, tmpl_h=th, cost="sad", search_min=lo, search_max=hi, camera_side=side, accept_threshold=thr,
-                         distance_kind=int(rng.integers(0, 3)))
+                         distance_kind=int(rng.integers(0, 3)), stride_x=sx, stride_y=sy)
     with_resolve = t % 4 == 0
     got = ctx.match_dense(left, right, p, mask=api.ALL_OUTPUTS | (_abi.OUT_RESOLVED_DISPARITY_U16 if with_resolve else 0))
     dense += ctx.last_kernel == "dense_sad_argmin_kernel"
