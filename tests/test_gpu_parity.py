@@ -573,3 +573,39 @@ def test_destroy_refuses_while_a_stream_is_open():
     st = c.stream(f, p, pairs_per_slot=2, n_slots=2, mask=_abi.OUT_DISPARITY_U16)
     c.close()            # closes the stream first
     assert st._h is None
+
+
+@pytest.mark.parametrize("cost,kw", [
+    ("sad", dict(search_max=60)),
+    ("sad", dict(search_min=-9, search_max=40)),            # negative disparities: the resolve reads RightIndex
+    ("ssd", dict(search_min=-5, search_max=50, accept_threshold=0.05)),
+    ("zncc", dict(search_min=-6, search_max=40)),
+    ("sad", dict(search_max=40, stride_x=2, stride_y=2)),   # direct-form kernel
+])
+def test_every_output_subset_gives_the_same_arrays(ctx, oracle, cost, kw):
+    """The library serves any subset of usv_outputs; arrays it needs itself (the winners the row resolve reads) come from the caller's
+    set or from scratch, depending on the subset. Every subset must reproduce the arrays of the full set, bit for bit."""
+    left, right = synth.make_pairs(2, 150, 30, 1, shift=8, noise_sigma=2.0, seed=77)
+    left[1, :, 70:] = 50
+    p = _abi.make_params(tmpl_w=8, tmpl_h=8, cost=cost, **kw)
+    u16 = _abi.OUT_RAW_COST_U16 if cost == "sad" else 0  # the 16-bit cost exists for SAD only
+    full_mask = api.ALL_OUTPUTS | u16 | _abi.OUT_RESOLVED_DISPARITY_U16
+    full = ctx.match_dense(left, right, p, mask=full_mask)
+    exp = oracle.match_dense(left, right, p)
+    for k in ("right_index", "raw_cost", "disparity_u16"):
+        assert np.array_equal(full[k], exp[k]), k
+    rng = np.random.default_rng(11)
+    bits = [_abi.OUT_MATCHES, _abi.OUT_RIGHT_INDEX, _abi.OUT_RAW_COST, _abi.OUT_SCORE, _abi.OUT_DISTANCE, _abi.OUT_DISTANCE_F32,
+            _abi.OUT_DISPARITY_U16] + ([u16] if u16 else [])
+    masks = [_abi.OUT_RESOLVED_DISPARITY_U16 | b for b in [0] + bits]
+    masks += [_abi.OUT_RESOLVED_DISPARITY_U16 | _abi.OUT_DISPARITY_U16 | u16,
+              _abi.OUT_RESOLVED_DISPARITY_U16 | _abi.OUT_DISPARITY_U16 | _abi.OUT_RAW_COST,
+              _abi.OUT_RESOLVED_DISPARITY_U16 | _abi.OUT_RIGHT_INDEX | _abi.OUT_RAW_COST,
+              _abi.OUT_RESOLVED_DISPARITY_U16 | _abi.OUT_RIGHT_INDEX | u16]
+    masks += [int(sum(b for b in bits if rng.random() < 0.4)) | (_abi.OUT_RESOLVED_DISPARITY_U16 if rng.random() < 0.7 else 0) for _ in range(16)]
+    for m in masks:
+        if m == 0:
+            continue
+        got = ctx.match_dense(left, right, p, mask=m)
+        for k, v in got.items():
+            assert v.tobytes() == full[k].tobytes(), (hex(m), k)
